@@ -1,0 +1,158 @@
+/*
+ * ipr_b200.h -- C ABI of libipr_b200.so: hand-written sm_100a CUDA kernels for the IPR-GAN hot path.
+ *
+ * The reference (dingsheng-ong/ipr-gan) is pure Python and has no FFI of its own; its "plugin"
+ * surface is the Python API of tools/*.py, models/wrappers.py and networks/*.py.  Each entry point
+ * below replaces the PyTorch op sequence of one reference function (cited file:line, paths relative
+ * to the reference root) and is what a ctypes binding inside that function would call
+ * (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are contiguous, NCHW, fp32 unless stated;
+ *   - the caller owns every buffer including workspaces; the library never allocates or frees
+ *     device memory and keeps no pointer after the call returns;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     never touches the default stream, and is CUDA-graph capturable;
+ *   - return value: 0 = OK; < 0 = argument error found on the host before any launch
+ *     (IPR_E_*); > 0 = cudaError_t reported by the launch.  ipr_strerror() names both.
+ *   - there is no CPU fallback.
+ */
+#ifndef IPR_B200_H
+#define IPR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPR_OK              0
+#define IPR_E_NULL         -1   /* a required pointer is NULL                       */
+#define IPR_E_SHAPE        -2   /* inconsistent / non-positive dimensions           */
+#define IPR_E_UNSUPPORTED  -3   /* valid but outside what the kernels cover         */
+#define IPR_E_ALIGN        -4   /* pointer alignment requirement violated           */
+#define IPR_E_WORKSPACE    -5   /* workspace too small                              */
+
+typedef void *ipr_stream_t;     /* cudaStream_t */
+
+int         ipr_version(void);
+const char *ipr_strerror(int code);
+/* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
+uint64_t    ipr_launch_count(void);
+
+/* ------------------------------------------------------------------ black-box trigger path */
+
+/* y = x; y[win] = y[win]*bg + (1-bg)*fg  with win = rows [row0,row0+s) x cols [col0,col0+s).
+ * Replaces PasteWatermark.forward (tools/paste_watermark.py:45-52) and
+ * RandomNoisePatch.forward (tools/random_noise_patch.py:38-45).  fg: (C,s,s), bg: (s,s).
+ * Bit-exact: two rounded ops (mul, then mul+add without FMA), as the reference's two in-place ops. */
+int ipr_paste_patch_f32(const float *x, float *y, const float *fg, const float *bg,
+                        int64_t batch, int channels, int height, int width,
+                        int size, int row0, int col0, ipr_stream_t stream);
+
+/* Fused trigger build for one training step: ywm = paste(x) as above AND xwm = transform_dist(z)
+ * in ONE launch (models/wrappers.py:49-51 with the DCGAN config's fn_inp/fn_out). */
+int ipr_trigger_pair_f32(const float *x, float *ywm, const float *fg, const float *bg,
+                         int64_t batch, int channels, int height, int width, int size, int row0, int col0,
+                         const float *z, float *xwm, int64_t z_numel, ipr_stream_t stream);
+
+/* out = 1*bg + (1-bg)*x[win]  -> (batch, C, s, s).
+ * Replaces PasteWatermark.apply_mask / RandomNoisePatch.apply_mask
+ * (tools/paste_watermark.py:54-61, tools/random_noise_patch.py:47-54). */
+int ipr_crop_patch_f32(const float *x, float *out, const float *bg,
+                       int64_t batch, int channels, int height, int width,
+                       int size, int row0, int col0, ipr_stream_t stream);
+
+/* out = z; out[:, mask[j]] = constant.  Replaces RandomBitMask.forward (tools/random_bitmask.py:12-15).
+ * mask: n int64 indices in [0, z_dim). */
+int ipr_bitmask_scatter_f32(const float *z, float *out, const int64_t *mask,
+                            int64_t batch, int z_dim, int n, float constant, ipr_stream_t stream);
+
+/* out = 0.5*(1+erf(z/sqrt(2)))*sqrt(2*pi).  Replaces TransformDist.forward (tools/transform_dist.py:9-11). */
+int ipr_transform_dist_f32(const float *z, float *out, int64_t numel, ipr_stream_t stream);
+
+/* out = z*(1-a) + a*w with a, w of length dim broadcast over the batch.
+ * Replaces TransformVar.forward (tools/transform_var.py:12-13). */
+int ipr_transform_var_f32(const float *z, float *out, const float *a, const float *w,
+                          int64_t batch, int dim, ipr_stream_t stream);
+
+/* ------------------------------------------------------------------ watermark reconstruction loss (SSIM) */
+
+/* Workspace (bytes) for ipr_ssim_fwd_bwd_f32 / ipr_ssim_per_sample_f32 on this shape. */
+size_t ipr_ssim_workspace_bytes(int64_t batch, int channels, int height, int width);
+
+/* loss = 1 - mean_{n,c} mean_{valid map} SSIM(x', y'),   x' = normalized ? (x+1)/2 : x  (same for y)
+ * dx   = grad_scale * d loss / d x            (y is a constant, models/wrappers.py:49-51)
+ * One pass over HBM: reads x and y once, writes dx once; the scalar loss is produced by a second,
+ * single-CTA launch that adds the per-CTA partial sums in a fixed order (deterministic).
+ * Replaces Loss.__call__ + ssim() (tools/loss.py:10-20, 82-85) -> pytorch_msssim.SSIM(data_range=1)
+ * forward AND its autograd backward.  11-tap sigma-1.5 valid separable window; H, W >= 11.
+ * dx may be NULL (forward only). */
+int ipr_ssim_fwd_bwd_f32(const float *x, const float *y, float *dx, float *loss,
+                         void *workspace, size_t workspace_bytes,
+                         int64_t batch, int channels, int height, int width,
+                         int normalized, float grad_scale, ipr_stream_t stream);
+
+/* out[n] = mean_{c, valid map} SSIM(x[n], y[n])  (data_range 1, no de-normalisation).
+ * Replaces pytorch_msssim.ssim(wm_x, wm_y, data_range=1, size_average=False)
+ * (experiments/image_generation.py:211). */
+int ipr_ssim_per_sample_f32(const float *x, const float *y, float *out,
+                            void *workspace, size_t workspace_bytes,
+                            int64_t batch, int channels, int height, int width, ipr_stream_t stream);
+
+/* ------------------------------------------------------------------ white-box signature */
+
+#define IPR_SIGN_MAX_LAYERS 64
+
+typedef struct {
+    const float *gamma;   /* normalisation-layer scale vector (device)               */
+    const float *sign;    /* +1/-1 signature vector (device)                         */
+    float       *grad;    /* d loss / d gamma destination (device) or NULL            */
+    int32_t      n;       /* channels in this layer                                  */
+    int32_t      reserved;
+} ipr_sign_layer_t;
+
+/* loss = sum_layers mean_c relu(gamma0 - gamma_c * sign_c);  grad_c = -grad_scale*sign_c/n_layer where active.
+ * accumulate != 0 adds into grad instead of overwriting (fused-arena use).
+ * `layers_host` is a HOST array of n_layers (<= IPR_SIGN_MAX_LAYERS) entries; it is copied into the
+ * kernel parameters, so it may be freed right after the call.
+ * Replaces SignLossModel.forward (tools/sign_model.py:42-49) and its backward. */
+int ipr_sign_loss_fwd_bwd_f32(const ipr_sign_layer_t *layers_host, int n_layers, float gamma0,
+                              float grad_scale, int accumulate, float *loss, ipr_stream_t stream);
+
+/* counts[0] = #{c : sign(gamma_c) != sign_c} (gamma == 0 counts as wrong), counts[1] = total bits.
+ * Replaces SignLossModel.compute_ber (tools/sign_model.py:51-60); integer, bit-exact. */
+int ipr_sign_ber_i32(const ipr_sign_layer_t *layers_host, int n_layers, int32_t *counts,
+                     ipr_stream_t stream);
+
+/* ------------------------------------------------------------------ verification (pHash p-value) */
+
+/* Bicubic up-sampling, align_corners=False, A=-0.75, border-replicated taps, with the operation
+ * order of torch's CPU kernel (F.interpolate(..., mode='bicubic'), tools/phash_pvalue.py:28-29):
+ * bit-exact against it (tests/test_phash.py).  x: (planes, hin, win) -> out: (planes, hout, wout). */
+int ipr_bicubic_resize_f32(const float *x, float *out, int64_t planes,
+                           int hin, int win, int hout, int wout, ipr_stream_t stream);
+
+/* 16x64 DCT matrix used by the PDQ hash (host side, double cos -> float). */
+void ipr_pdq_dct_matrix_host(float *d_host);
+
+/* hash[n] = 256-bit PDQ hash (8 x uint32, bit k = word k/32, bit k%32; k = 16*i+j of the DCT block)
+ * of image n after the reference's float->uint8 conversion (x*255 truncated, wrapped to 0..255).
+ * img: (batch, 3, height, width) fp32; 8 <= height, width <= 64 (larger: IPR_E_UNSUPPORTED).
+ * dct: device copy of ipr_pdq_dct_matrix_host().  coeffs (optional, may be NULL): (batch, 256) DCT block.
+ * Replaces compute_hash (tools/phash_pvalue.py:7-17) -> pdqhash.compute. */
+int ipr_pdq_hash_f32(const float *img, uint32_t *hash, float *coeffs, const float *dct,
+                     int64_t batch, int height, int width, ipr_stream_t stream);
+
+/* r[n] = 256 - popcount(hx[n] ^ hy[n]);  p[n] = ptable[r[n]]   (ptable: 257 fp32 entries
+ * 1 - Binom(256, 1/2).cdf(r-1), built on the host exactly as tools/phash_pvalue.py:36 does).
+ * Replaces tools/phash_pvalue.py:34-37. */
+int ipr_hash_pvalue(const uint32_t *hx, const uint32_t *hy, const float *ptable,
+                    float *p, int32_t *r, int64_t batch, ipr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPR_B200_H */

@@ -1,0 +1,458 @@
+// ssim.cu -- watermark reconstruction loss: SSIM (11-tap sigma-1.5 valid separable Gaussian window)
+// forward AND backward in one pass over HBM.
+//
+// Replaces tools/loss.py:10-20,82-85 -> pytorch_msssim.SSIM(data_range=1) (10 depthwise conv2d +
+// ~20 elementwise kernels forward, about twice that in autograd backward) with ONE kernel that reads
+// x and y once and writes d(loss)/dx once:   algorithmic traffic 36*B*H*W bytes (3 tensors x 3 ch x 4 B).
+//
+// Layout / tiling
+//   * one CTA = one 32x32 tile of dX for NP consecutive (n,c) planes; halo recomputed per tile
+//     (a 32x32 image is a single tile with no halo, the DCGAN case);
+//   * shared memory holds interleaved (x,y) pairs so that every pass moves 64-bit words:
+//       pass 1 (vertical)   : (x,y) -> sum g*(x,y), sum g*(x^2+y^2, x*y)
+//       pass 2 (horizontal) : -> mu_x, mu_y, E[x^2+y^2], E[xy] -> SSIM map S and dS/dp, dS/dq, dS/dr
+//       pass 3 (vertical^T) , pass 4 (horizontal^T): full correlation of the three derivative maps,
+//       epilogue dX = coef * (Fp + 2 x Fq + y Fr), 128-bit stores;
+//   * each thread keeps a sliding window of L+10 inputs in registers and produces L outputs, so the
+//     11-tap filter costs (L+10)/L shared loads per output instead of 11; taps are compile-time
+//     immediates (FFMA with immediate operand).
+//   * sigma_x^2 + sigma_y^2 only ever appears as a sum, so x^2 and y^2 are filtered together
+//     (4 filtered quantities instead of 5).
+// The SSIM-map sum is reduced per plane inside the CTA (fixed order) into a workspace and a second
+// single-CTA launch adds the partials in a fixed order: results are run-to-run deterministic.
+#include "ipr_common.cuh"
+
+namespace {
+
+constexpr int RAD = 10;            // window - 1
+constexpr int TILE = 32;           // dX tile edge
+constexpr int LCH = 8;             // outputs per thread per pass (sliding-window length)
+constexpr float SSIM_C1 = 1.0e-4f; // (0.01 * 1)^2
+constexpr float SSIM_C2 = 9.0e-4f; // (0.03 * 1)^2
+
+// exp(-(i-5)^2 / (2*1.5^2)) / sum, evaluated in fp32 exactly as pytorch_msssim._fspecial_gauss_1d does
+// (tests/test_ssim_oracle.py checks these bit patterns against torch).
+__device__ constexpr float kTap[11] = {
+    0x1.0d957p-10f, 0x1.f1fe02p-8f, 0x1.26eb18p-5f, 0x1.bff0fep-4f, 0x1.b43c3ep-3f, 0x1.10656p-2f,
+    0x1.b43c3ep-3f, 0x1.bff0fep-4f, 0x1.26eb18p-5f, 0x1.f1fe02p-8f, 0x1.0d957p-10f};
+
+struct SsimParams {
+    const float *x, *y;
+    float *dx;
+    float *partial;        // [planes][tiles]
+    long long planes;
+    int H, W, Hv, Wv;      // Hv = H-10, Wv = W-10 (valid SSIM map)
+    int tiles_r, tiles_c;
+    int np;                // planes per CTA
+    int normalized;
+    float coef;            // -grad_scale * (normalized ? .5 : 1) / (planes*Hv*Wv)
+};
+
+struct Geom {
+    int r0, r1, c0, c1;    // dX tile (global coords)
+    int i0, i1, j0, j1;    // SSIM-map rows/cols needed by this tile
+    int IR, IC, SR, SC, OR, OC;
+    int pP, pD;            // pitches (in elements) of the input-pair and map arrays, both odd
+};
+
+__device__ __forceinline__ Geom make_geom(const SsimParams &p, int tile)
+{
+    Geom g;
+    const int tr = tile / p.tiles_c, tc = tile - tr * p.tiles_c;
+    g.r0 = tr * TILE; g.r1 = min(p.H, g.r0 + TILE);
+    g.c0 = tc * TILE; g.c1 = min(p.W, g.c0 + TILE);
+    g.i0 = max(0, g.r0 - RAD); g.i1 = min(p.Hv, g.r1);
+    g.j0 = max(0, g.c0 - RAD); g.j1 = min(p.Wv, g.c1);
+    g.SR = g.i1 - g.i0; g.SC = g.j1 - g.j0;
+    g.IR = g.SR + RAD;  g.IC = g.SC + RAD;
+    g.OR = g.r1 - g.r0; g.OC = g.c1 - g.c0;
+    g.pP = g.IC | 1;
+    g.pD = g.SC | 1;
+    return g;
+}
+
+// shared-memory carve-up per plane slot (units: floats)
+struct Carve {
+    int P, Va, Vb, Dpq, Dr, Epq, Er, total;
+};
+__host__ __device__ inline Carve make_carve(int IR, int SR, int OR, int pP, int pD)
+{
+    Carve c;
+    int o = 0;
+    c.P = o;   o += 2 * IR * pP;
+    c.Dpq = o; o += 2 * SR * pD;
+    c.Dr = o;  o += SR * pD;
+    o = (o + 1) & ~1;
+    // V (passes 1-2) and E (passes 3-4) are never live together: alias them
+    const int v = 4 * SR * pP, e = 3 * OR * pD + 1;
+    c.Va = o; c.Vb = o + 2 * SR * pP;
+    c.Epq = o; c.Er = o + 2 * OR * pD;
+    c.Er = (c.Er + 1) & ~1;
+    o += (v > e ? v : e) + 2;
+    c.total = (o + 1) & ~1;
+    return c;
+}
+
+template <bool WITH_GRAD>
+__global__ void __launch_bounds__(256)
+ssim_tile_kernel(const SsimParams p)
+{
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float red[32];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const Geom g = make_geom(p, blockIdx.y);
+    const Carve cv = make_carve(g.IR, g.SR, g.OR, g.pP, g.pD);
+    const long long plane0 = (long long)blockIdx.x * p.np;
+    const int np = p.np;
+    const size_t plane_elems = (size_t)p.H * p.W;
+
+    // ---------------- phase 0: global -> shared, interleaving (x, y) and de-normalising
+    {
+        const bool fast = (g.IC == p.W) && ((p.W & 3) == 0) && ((plane_elems & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y)) & 15) == 0;
+        if (fast) {
+            const int w4 = g.IC >> 2, per = g.IR * w4;
+            for (int e = tid; e < np * per; e += nth) {
+                const int slot = e / per, rem = e - slot * per;
+                const int rr = rem / w4, c4 = rem - rr * w4;
+                const long long pl = min(plane0 + slot, p.planes - 1);
+                const size_t off = (size_t)pl * plane_elems + (size_t)(g.i0 + rr) * p.W + (c4 << 2);
+                float4 a = ipr_ldg_stream4(reinterpret_cast<const float4 *>(p.x + off));
+                float4 b = ipr_ldg_stream4(reinterpret_cast<const float4 *>(p.y + off));
+                if (p.normalized) {
+                    a.x = (a.x + 1.f) * .5f; a.y = (a.y + 1.f) * .5f; a.z = (a.z + 1.f) * .5f; a.w = (a.w + 1.f) * .5f;
+                    b.x = (b.x + 1.f) * .5f; b.y = (b.y + 1.f) * .5f; b.z = (b.z + 1.f) * .5f; b.w = (b.w + 1.f) * .5f;
+                }
+                float2 *dst = reinterpret_cast<float2 *>(smem + slot * cv.total + cv.P) + rr * g.pP + (c4 << 2);
+                dst[0] = make_float2(a.x, b.x); dst[1] = make_float2(a.y, b.y);
+                dst[2] = make_float2(a.z, b.z); dst[3] = make_float2(a.w, b.w);
+            }
+        } else {
+            const int per = g.IR * g.IC;
+            for (int e = tid; e < np * per; e += nth) {
+                const int slot = e / per, rem = e - slot * per;
+                const int rr = rem / g.IC, cc = rem - rr * g.IC;
+                const long long pl = min(plane0 + slot, p.planes - 1);
+                const size_t off = (size_t)pl * plane_elems + (size_t)(g.i0 + rr) * p.W + (g.j0 + cc);
+                float a = __ldg(p.x + off), b = __ldg(p.y + off);
+                if (p.normalized) { a = (a + 1.f) * .5f; b = (b + 1.f) * .5f; }
+                reinterpret_cast<float2 *>(smem + slot * cv.total + cv.P)[rr * g.pP + cc] = make_float2(a, b);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- pass 1: vertical filter of (x,y) and (x^2+y^2, xy); lanes -> columns
+    {
+        const int nch = (g.SR + LCH - 1) / LCH, per = g.IC * nch;
+        for (int it = tid; it < np * per; it += nth) {
+            const int slot = it / per, rem = it - slot * per;
+            const int ch = rem / g.IC, col = rem - ch * g.IC;
+            const int rb = ch * LCH;
+            const float2 *src = reinterpret_cast<const float2 *>(smem + slot * cv.total + cv.P) + col;
+            float2 w[LCH + RAD], q[LCH + RAD];
+#pragma unroll
+            for (int t = 0; t < LCH + RAD; t++) {
+                w[t] = src[min(rb + t, g.IR - 1) * g.pP];
+                q[t] = make_float2(fmaf(w[t].x, w[t].x, w[t].y * w[t].y), w[t].x * w[t].y);
+            }
+            float2 *va = reinterpret_cast<float2 *>(smem + slot * cv.total + cv.Va) + col;
+            float2 *vb = reinterpret_cast<float2 *>(smem + slot * cv.total + cv.Vb) + col;
+#pragma unroll
+            for (int o = 0; o < LCH; o++) {
+                float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    a.x = fmaf(kTap[k], w[o + k].x, a.x); a.y = fmaf(kTap[k], w[o + k].y, a.y);
+                    b.x = fmaf(kTap[k], q[o + k].x, b.x); b.y = fmaf(kTap[k], q[o + k].y, b.y);
+                }
+                if (rb + o < g.SR) { va[(rb + o) * g.pP] = a; vb[(rb + o) * g.pP] = b; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- pass 2: horizontal filter + SSIM map + derivative maps; lanes -> rows
+    float ssum[4] = {0.f, 0.f, 0.f, 0.f};   // per plane slot (np <= 4)
+    {
+        const int nch = (g.SC + LCH - 1) / LCH, per = g.SR * nch;
+        for (int it = tid; it < np * per; it += nth) {
+            const int slot = it / per, rem = it - slot * per;
+            const int ch = rem / g.SR, row = rem - ch * g.SR;
+            const int cb = ch * LCH;
+            const float2 *va = reinterpret_cast<const float2 *>(smem + slot * cv.total + cv.Va) + row * g.pP;
+            const float2 *vb = reinterpret_cast<const float2 *>(smem + slot * cv.total + cv.Vb) + row * g.pP;
+            float2 wa[LCH + RAD], wb[LCH + RAD];
+#pragma unroll
+            for (int t = 0; t < LCH + RAD; t++) {
+                const int cc = min(cb + t, g.IC - 1);
+                wa[t] = va[cc]; wb[t] = vb[cc];
+            }
+            float2 *dpq = reinterpret_cast<float2 *>(smem + slot * cv.total + cv.Dpq) + row * g.pD;
+            float *dr = smem + slot * cv.total + cv.Dr + row * g.pD;
+            const bool row_owned = (g.i0 + row) >= g.r0;       // (< r1 holds because i1 <= r1)
+            float acc = 0.f;
+#pragma unroll
+            for (int o = 0; o < LCH; o++) {
+                float mx = 0.f, my = 0.f, e2 = 0.f, exy = 0.f;
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    mx = fmaf(kTap[k], wa[o + k].x, mx);  my = fmaf(kTap[k], wa[o + k].y, my);
+                    e2 = fmaf(kTap[k], wb[o + k].x, e2);  exy = fmaf(kTap[k], wb[o + k].y, exy);
+                }
+                const float mxx = mx * mx, myy = my * my, mxy = mx * my;
+                const float A1 = 2.f * mxy + SSIM_C1;
+                const float B1 = mxx + myy + SSIM_C1;
+                const float A2 = 2.f * (exy - mxy) + SSIM_C2;
+                const float B2 = (e2 - mxx - myy) + SSIM_C2;
+                const float iB1 = 1.0f / B1, iB2 = 1.0f / B2;
+                const float iB12 = iB1 * iB2;
+                const float S = A1 * A2 * iB12;
+                if (cb + o < g.SC) {
+                    if (WITH_GRAD) {
+                        const float dS_dq = -S * iB2;
+                        const float dS_dr = 2.f * A1 * iB12;
+                        const float dS_dp = 2.f * my * (A2 - A1) * iB12 + 2.f * mx * S * (iB2 - iB1);
+                        dpq[cb + o] = make_float2(dS_dp, dS_dq);
+                        dr[cb + o] = dS_dr;
+                    }
+                    if (row_owned && (g.j0 + cb + o) >= g.c0) acc += S;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++) if (s == slot) ssum[s] += acc;
+        }
+    }
+    // per-plane partial sums of the SSIM map (fixed-order block reduction)
+    for (int s = 0; s < np; s++) {
+        const float tot = ipr_block_sum(ssum[s], red);
+        if (tid == 0 && plane0 + s < p.planes)
+            p.partial[(size_t)(plane0 + s) * gridDim.y + blockIdx.y] = tot;
+    }
+    if (!WITH_GRAD) return;
+    __syncthreads();
+
+    // ---------------- pass 3: vertical transposed filter of (dp,dq,dr); lanes -> columns
+    {
+        const int nch = (g.OR + LCH - 1) / LCH, per = g.SC * nch;
+        for (int it = tid; it < np * per; it += nth) {
+            const int slot = it / per, rem = it - slot * per;
+            const int ch = rem / g.SC, col = rem - ch * g.SC;
+            const int ob = ch * LCH;                     // local output row
+            const float2 *dpq = reinterpret_cast<const float2 *>(smem + slot * cv.total + cv.Dpq) + col;
+            const float *dr = smem + slot * cv.total + cv.Dr + col;
+            float2 w[LCH + RAD]; float wr[LCH + RAD];
+#pragma unroll
+            for (int t = 0; t < LCH + RAD; t++) {
+                const int li = (g.r0 + ob + t - RAD) - g.i0;     // local SSIM-map row feeding output rows
+                const bool ok = (li >= 0) && (li < g.SR);
+                const int lc = ok ? li : 0;
+                const float2 v = dpq[lc * g.pD]; const float vr = dr[lc * g.pD];
+                w[t] = ok ? v : make_float2(0.f, 0.f); wr[t] = ok ? vr : 0.f;
+            }
+            float2 *epq = reinterpret_cast<float2 *>(smem + slot * cv.total + cv.Epq) + col;
+            float *er = smem + slot * cv.total + cv.Er + col;
+#pragma unroll
+            for (int o = 0; o < LCH; o++) {
+                float2 a = make_float2(0.f, 0.f); float b = 0.f;
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    a.x = fmaf(kTap[k], w[o + k].x, a.x); a.y = fmaf(kTap[k], w[o + k].y, a.y);
+                    b = fmaf(kTap[k], wr[o + k], b);
+                }
+                if (ob + o < g.OR) { epq[(ob + o) * g.pD] = a; er[(ob + o) * g.pD] = b; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- pass 4: horizontal transposed filter + epilogue; lanes -> rows
+    {
+        const int nch = (g.OC + LCH - 1) / LCH, per = g.OR * nch;
+        const bool vec_ok = ((p.W & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dx) & 15) == 0);
+        for (int it = tid; it < np * per; it += nth) {
+            const int slot = it / per, rem = it - slot * per;
+            const int ch = rem / g.OR, row = rem - ch * g.OR;
+            const int ob = ch * LCH;                     // local output col
+            if (plane0 + slot >= p.planes) continue;
+            const float2 *epq = reinterpret_cast<const float2 *>(smem + slot * cv.total + cv.Epq) + row * g.pD;
+            const float *er = smem + slot * cv.total + cv.Er + row * g.pD;
+            float2 w[LCH + RAD]; float wr[LCH + RAD];
+#pragma unroll
+            for (int t = 0; t < LCH + RAD; t++) {
+                const int lj = (g.c0 + ob + t - RAD) - g.j0;
+                const bool ok = (lj >= 0) && (lj < g.SC);
+                const int lc = ok ? lj : 0;
+                const float2 v = epq[lc]; const float vr = er[lc];
+                w[t] = ok ? v : make_float2(0.f, 0.f); wr[t] = ok ? vr : 0.f;
+            }
+            const float2 *pin = reinterpret_cast<const float2 *>(smem + slot * cv.total + cv.P) +
+                                (g.r0 + row - g.i0) * g.pP + (g.c0 + ob - g.j0);
+            float outv[LCH];
+#pragma unroll
+            for (int o = 0; o < LCH; o++) {
+                float fp = 0.f, fq = 0.f, fr = 0.f;
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    fp = fmaf(kTap[k], w[o + k].x, fp); fq = fmaf(kTap[k], w[o + k].y, fq);
+                    fr = fmaf(kTap[k], wr[o + k], fr);
+                }
+                float2 xy = make_float2(0.f, 0.f);
+                if (ob + o < g.OC) xy = pin[o];
+                outv[o] = p.coef * (fp + 2.f * xy.x * fq + xy.y * fr);
+            }
+            float *dst = p.dx + (size_t)(plane0 + slot) * plane_elems + (size_t)(g.r0 + row) * p.W + (g.c0 + ob);
+            if (vec_ok && ob + LCH <= g.OC) {
+                ipr_stg_stream4(reinterpret_cast<float4 *>(dst), make_float4(outv[0], outv[1], outv[2], outv[3]));
+                ipr_stg_stream4(reinterpret_cast<float4 *>(dst) + 1, make_float4(outv[4], outv[5], outv[6], outv[7]));
+            } else {
+#pragma unroll
+                for (int o = 0; o < LCH; o++) if (ob + o < g.OC) dst[o] = outv[o];
+            }
+        }
+    }
+}
+
+// loss = 1 - (sum of all partials) / count        (single CTA, fixed order)
+__global__ void __launch_bounds__(1024)
+ssim_finalize_loss_kernel(const float *__restrict__ partial, long long n, float inv_count, float *__restrict__ loss)
+{
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+    const float tot = ipr_block_sum(acc, red);
+    if (threadIdx.x == 0) *loss = 1.0f - tot * inv_count;
+}
+
+// out[n] = (sum over the sample's C planes and tiles) / (C*Hv*Wv)
+__global__ void __launch_bounds__(256)
+ssim_finalize_sample_kernel(const float *__restrict__ partial, long long batch, int per_sample, float inv_count,
+                            float *__restrict__ out)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= batch) return;
+    const float *src = partial + n * per_sample;
+    float acc = 0.f;
+    for (int i = 0; i < per_sample; i++) acc += src[i];
+    out[n] = acc * inv_count;
+}
+
+struct Plan {
+    int tiles_r, tiles_c, np, threads;
+    size_t smem;
+};
+
+Plan make_plan(int H, int W)
+{
+    Plan pl;
+    pl.tiles_r = (H + TILE - 1) / TILE;
+    pl.tiles_c = (W + TILE - 1) / TILE;
+    // worst-case tile geometry on this image
+    const int maxOR = H < TILE ? H : TILE, maxOC = W < TILE ? W : TILE;
+    int maxSR = 0, maxSC = 0;
+    for (int t = 0; t < pl.tiles_r; t++) {
+        int r0 = t * TILE, r1 = r0 + TILE < H ? r0 + TILE : H;
+        int i0 = r0 - RAD > 0 ? r0 - RAD : 0, i1 = r1 < H - RAD ? r1 : H - RAD;
+        if (i1 - i0 > maxSR) maxSR = i1 - i0;
+    }
+    for (int t = 0; t < pl.tiles_c; t++) {
+        int c0 = t * TILE, c1 = c0 + TILE < W ? c0 + TILE : W;
+        int j0 = c0 - RAD > 0 ? c0 - RAD : 0, j1 = c1 < W - RAD ? c1 : W - RAD;
+        if (j1 - j0 > maxSC) maxSC = j1 - j0;
+    }
+    const Carve cv = make_carve(maxSR + RAD, maxSR, maxOR, (maxSC + RAD) | 1, maxSC | 1);
+    const size_t per_plane = (size_t)cv.total * sizeof(float);
+    // small images: several planes per CTA so that every pass has enough work items for its warps
+    const long long pix = (long long)H * W;
+    pl.np = pix <= 1024 ? 2 : 1;
+    pl.threads = 128;
+    if (pix > 1024) pl.threads = 256;
+    pl.smem = per_plane * pl.np;
+    return pl;
+}
+
+int check_common(const float *x, const float *y, int64_t batch, int C, int H, int W)
+{
+    IPR_REQUIRE(x && y, IPR_E_NULL);
+    IPR_REQUIRE(batch > 0 && C > 0 && H > 0 && W > 0, IPR_E_SHAPE);
+    IPR_REQUIRE(H > RAD && W > RAD, IPR_E_UNSUPPORTED);   // the window must fit (pytorch_msssim skips the pass otherwise)
+    IPR_REQUIRE((long long)batch * C < (1LL << 31), IPR_E_UNSUPPORTED);
+    return IPR_OK;
+}
+
+template <bool WITH_GRAD>
+int launch_tiles(const SsimParams &p, const Plan &pl, cudaStream_t st)
+{
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[WITH_GRAD]) {
+        cudaError_t e = cudaFuncSetAttribute(ssim_tile_kernel<WITH_GRAD>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_done[WITH_GRAD] = true;
+    }
+    const long long groups = (p.planes + pl.np - 1) / pl.np;
+    IPR_REQUIRE(pl.tiles_r * pl.tiles_c <= 65535, IPR_E_UNSUPPORTED);
+    dim3 grid((unsigned)groups, (unsigned)(pl.tiles_r * pl.tiles_c));
+    ssim_tile_kernel<WITH_GRAD><<<grid, pl.threads, pl.smem, st>>>(p);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+}  // namespace
+
+extern "C" size_t ipr_ssim_workspace_bytes(int64_t batch, int channels, int height, int width)
+{
+    if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return 0;
+    const size_t tiles = (size_t)((height + TILE - 1) / TILE) * ((width + TILE - 1) / TILE);
+    return (size_t)batch * channels * tiles * sizeof(float);
+}
+
+extern "C" int ipr_ssim_fwd_bwd_f32(const float *x, const float *y, float *dx, float *loss,
+                                    void *workspace, size_t workspace_bytes,
+                                    int64_t batch, int channels, int height, int width,
+                                    int normalized, float grad_scale, ipr_stream_t stream)
+{
+    int rc = check_common(x, y, batch, channels, height, width);
+    if (rc != IPR_OK) return rc;
+    IPR_REQUIRE(loss && workspace, IPR_E_NULL);
+    IPR_REQUIRE(workspace_bytes >= ipr_ssim_workspace_bytes(batch, channels, height, width), IPR_E_WORKSPACE);
+    const Plan pl = make_plan(height, width);
+    SsimParams p;
+    p.x = x; p.y = y; p.dx = dx; p.partial = (float *)workspace;
+    p.planes = (long long)batch * channels;
+    p.H = height; p.W = width; p.Hv = height - RAD; p.Wv = width - RAD;
+    p.tiles_r = pl.tiles_r; p.tiles_c = pl.tiles_c; p.np = pl.np; p.normalized = normalized;
+    const double count = (double)p.planes * p.Hv * p.Wv;
+    p.coef = (float)(-(double)grad_scale * (normalized ? 0.5 : 1.0) / count);
+    rc = dx ? launch_tiles<true>(p, pl, ipr_cu(stream)) : launch_tiles<false>(p, pl, ipr_cu(stream));
+    if (rc != IPR_OK) return rc;
+    const long long n = p.planes * pl.tiles_r * pl.tiles_c;
+    ssim_finalize_loss_kernel<<<1, 1024, 0, ipr_cu(stream)>>>(p.partial, n, (float)(1.0 / count), loss);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" int ipr_ssim_per_sample_f32(const float *x, const float *y, float *out,
+                                       void *workspace, size_t workspace_bytes,
+                                       int64_t batch, int channels, int height, int width, ipr_stream_t stream)
+{
+    int rc = check_common(x, y, batch, channels, height, width);
+    if (rc != IPR_OK) return rc;
+    IPR_REQUIRE(out && workspace, IPR_E_NULL);
+    IPR_REQUIRE(workspace_bytes >= ipr_ssim_workspace_bytes(batch, channels, height, width), IPR_E_WORKSPACE);
+    const Plan pl = make_plan(height, width);
+    SsimParams p;
+    p.x = x; p.y = y; p.dx = nullptr; p.partial = (float *)workspace;
+    p.planes = (long long)batch * channels;
+    p.H = height; p.W = width; p.Hv = height - RAD; p.Wv = width - RAD;
+    p.tiles_r = pl.tiles_r; p.tiles_c = pl.tiles_c; p.np = pl.np; p.normalized = 0;
+    p.coef = 0.f;
+    rc = launch_tiles<false>(p, pl, ipr_cu(stream));
+    if (rc != IPR_OK) return rc;
+    const int per_sample = channels * pl.tiles_r * pl.tiles_c;
+    const float inv = (float)(1.0 / ((double)channels * p.Hv * p.Wv));
+    ssim_finalize_sample_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, ipr_cu(stream)>>>(
+        p.partial, batch, per_sample, inv, out);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}

@@ -1,0 +1,69 @@
+"""Hinge-loss DCGAN step with the reference's interface (models/dcgan.py:7-78): ``update_d(data)`` with
+``real_sample`` / ``latent``, ``update_g(data, update=True)`` re-using the generator graph built in
+``forward_d``, ``get_metrics()`` -> dict of floats, ``_modules`` = G, D, optG, optD."""
+import torch
+from torch import optim
+from torch.nn import functional as F
+
+import networks
+from models.core import Model
+from models.util import Replica
+
+
+class DCGAN(Model):
+    def __init__(self, config, device=[torch.device("cpu"), ]):
+        super().__init__()
+        self.device = device
+        ids = [d.index for d in device]
+        self.G = Replica(getattr(networks, config.G)().to(device[0]), device_ids=ids)
+        self.D = Replica(getattr(networks, config.D)().to(device[0]), device_ids=ids)
+        self.G.train()
+        self.D.train()
+
+        make_opt = getattr(optim, config.opt)
+        kwargs = config.opt_param.to_dict()
+        self.optG = make_opt(self.G.parameters(), **kwargs)
+        self.optD = make_opt(self.D.parameters(), **kwargs)
+        self._modules.update(G=self.G, D=self.D, optG=self.optG, optD=self.optD)
+
+    # ---- losses (models/dcgan.py:31-40)
+    def compute_d_loss(self):
+        self.LossR = F.relu(1.0 - self.real_logits).mean()
+        self.LossF = F.relu(1.0 + self.fake_logits).mean()
+        self.LossD = self.LossR + self.LossF
+
+    def compute_g_loss(self):
+        self.LossA = -self.gen_logits.mean()
+        self.LossG = self.LossA
+
+    # ---- forwards (models/dcgan.py:42-52)
+    def forward_d(self, data):
+        self.latent = data["latent"]
+        self.real_sample = data["real_sample"]
+        self.fake_sample = self.G(self.latent)
+        self.real_logits = self.D(self.real_sample)
+        self.fake_logits = self.D(self.fake_sample.detach())
+
+    def forward_g(self, data):
+        self.generated = data["fake_sample"]
+        self.gen_logits = self.D(self.generated)
+
+    def get_metrics(self):
+        vals = torch.stack([self.LossD, self.LossR, self.LossF, self.LossG, self.LossA]).tolist()  # one D2H copy
+        return dict(zip(("D/Sum", "D/Real", "D/Fake", "G/Sum", "G/Adv"), vals))
+
+    # ---- updates (models/dcgan.py:63-78)
+    def update_d(self, data):
+        self.forward_d(data)
+        self.compute_d_loss()
+        self.optD.zero_grad()
+        self.LossD.backward()
+        self.optD.step()
+
+    def update_g(self, data, update=True):
+        self.forward_g(data)
+        self.compute_g_loss()
+        if update:
+            self.optG.zero_grad()
+            self.LossG.backward()
+            self.optG.step()
