@@ -152,6 +152,58 @@ int ipr_pdq_hash_f32(const float *img, uint32_t *hash, float *coeffs, const floa
 int ipr_hash_pvalue(const uint32_t *hx, const uint32_t *hy, const float *ptable,
                     float *p, int32_t *r, int64_t batch, ipr_stream_t stream);
 
+
+/* ------------------------------------------------------------------ dense layers (tcgen05 implicit GEMM) */
+
+#define IPR_TG_MAX_TAPS   16
+#define IPR_TG_MAX_PHASES 4
+
+/* epilogue modes */
+#define IPR_EPI_LINEAR      0   /* out = acc / sigma                          -> bf16 NHWC (+ optional column stats) */
+#define IPR_EPI_BIAS_LRELU  1   /* out = lrelu(acc / sigma + bias[n], slope)  -> bf16 NHWC                           */
+#define IPR_EPI_MASK        2   /* out = acc / sigma * (mask[m,n] > 0 ? 1 : slope) -> bf16 NHWC (activation backward) */
+#define IPR_EPI_TANH_NCHW   3   /* out = tanh(acc), columns < n_valid          -> fp32 NCHW                          */
+#define IPR_EPI_LINEAR_F32  4   /* out = acc / sigma                          -> fp32 NHWC                           */
+#define IPR_EPI_LINEAR_NCHW 5   /* out = acc / sigma, columns < n_valid        -> fp32 NCHW                          */
+
+/* One "tap GEMM": for every phase p and output pixel m of a virtual grid (a_n x q_h x q_w)
+ *     acc[m, n] = sum_{t < n_taps} sum_{c < a_c} A[img(m), s*qh(m) + dh[p][t], s*qw(m) + dw[p][t], c] * B[p][n][t*a_c + c]
+ * with A an NHWC bf16 activation tensor read by TMA boxes (out-of-range pixels read as zero = padding) and B
+ * packed bf16 weights.  s = 1 for a_parity == 0; for a_parity == 1 the tensor is addressed through its four
+ * (row parity, column parity) sub-grids: tap_map[p][t] = 2*row_parity + col_parity and dh/dw are offsets in the
+ * half-resolution grid (stride-2 convolution).  Output pixel of m: (qh*out_sh + out_oh[p], qw*out_sw + out_ow[p]).
+ * This one kernel serves Conv2d k3s1 / k4s2 forward, ConvTranspose2d k4s2 (4 output-parity phases) and k3s1 forward,
+ * their data gradients, and Linear (q_h = q_w = 1).
+ * Replaces the cuDNN / cuBLAS calls under networks/conv_generator.py:8,13,21 and networks/sn_discriminator.py:9-21. */
+typedef struct {
+    const void *a;                 /* bf16 NHWC activations, 16-byte aligned                         */
+    int32_t a_n, a_h, a_w, a_c;    /* a_c multiple of 64                                             */
+    int32_t a_parity;
+    int32_t q_h, q_w;              /* virtual output grid per image; q_w*q_h divides or is divided by 128 */
+    const void *b;                 /* bf16 [n_phases][n_total][n_taps*a_c]                           */
+    int32_t n_total;               /* padded N (multiple of block_n)                                 */
+    int32_t block_n;               /* 16, 32, 64 or 128                                              */
+    int32_t n_phases, n_taps;
+    int8_t  tap_map[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
+    int8_t  tap_dh[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
+    int8_t  tap_dw[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
+    int32_t epi_mode;
+    float   slope;
+    const float *sigma;            /* optional device scalar: acc is divided by it (spectral norm)   */
+    const float *bias;             /* optional fp32 [n_total]                                        */
+    const void  *mask;             /* IPR_EPI_MASK: bf16 tensor with the layout of `out`             */
+    void   *out;
+    int32_t out_h, out_w, out_c;   /* output tensor (a_n, out_h, out_w, out_c) NHWC (or NCHW fp32)   */
+    int32_t out_sh, out_sw;
+    int8_t  out_oh[IPR_TG_MAX_PHASES], out_ow[IPR_TG_MAX_PHASES];
+    int32_t n_valid;               /* columns >= n_valid are not stored                              */
+    float  *stats;                 /* optional [m_tiles*n_phases*4][2][n_total] per-warp column sums / sums of squares */
+} ipr_tapgemm_t;
+
+/* number of M tiles (rows of `stats` = 4 * n_phases * this) */
+int ipr_tapgemm_m_tiles(const ipr_tapgemm_t *d_host);
+int ipr_tapgemm_bf16(const ipr_tapgemm_t *d_host, ipr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ SIGNATURES = {
     "ipr_pdq_dct_matrix_host": (None, [c_ptr]),
     "ipr_pdq_hash_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr]),
     "ipr_hash_pvalue": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ipr_tapgemm_m_tiles": (c_int, [c_ptr]),
+    "ipr_tapgemm_bf16": (c_int, [c_ptr, c_ptr]),
 }
 
 _lib = None

@@ -1,0 +1,378 @@
+// gemm_tc.cu -- "tap GEMM": implicit-GEMM convolution / transposed convolution / linear layers on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+//   acc[m, n] = sum_taps sum_c A[pixel(m) + tap offset, c] * B[n, tap*C + c]
+//
+// * A tiles are fetched straight from the NHWC bf16 activation tensor by 4-D TMA boxes
+//   (channels x width x rows x images); a tap is just a shifted box, and the zero padding of the
+//   convolution is TMA's out-of-bounds fill -- no im2col buffer ever exists in HBM.
+// * stride-2 convolutions address the input through its four (row, column) parity sub-grids, each
+//   described by its own tensor map; k4s2 transposed convolutions run as four output-parity phases of
+//   2x2 taps (blockIdx.z), so no multiplication by an inserted zero is ever issued.
+// * 128-byte swizzled K-major smem tiles feed tcgen05.mma (M=128, N=BLOCK_N, K=16 per instruction);
+//   one elected thread issues, tcgen05.commit releases smem stages / signals the epilogue.
+// * warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2-5 epilogue
+//   (tcgen05.ld 32 lanes x 32 columns, fused 1/sigma, bias, LeakyReLU / activation-gradient mask /
+//   tanh, bf16 pack, per-column sum and sum-of-squares for BatchNorm).
+// * two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's epilogue
+//   overlaps the other's main loop.
+#include "ipr_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // bf16 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 192;
+
+struct TgParams {
+    int a_n, q_h, q_w, tile_h, tile_imgs, tiles_per_img, m_tiles;
+    int a_c, c_chunks, n_taps, n_total;
+    int8_t tap_map[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
+    int8_t tap_dh[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
+    int8_t tap_dw[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
+    int epi_mode;
+    float slope;
+    const float *sigma;
+    const float *bias;
+    const __nv_bfloat16 *mask;
+    void *out;
+    int out_h, out_w, out_c, out_sh, out_sw;
+    int8_t out_oh[IPR_TG_MAX_PHASES], out_ow[IPR_TG_MAX_PHASES];
+    int n_valid;
+    float *stats;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS)
+tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+               const __grid_constant__ CUtensorMap mapB, const TgParams p)
+{
+    constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr int CH = BLOCK_N >= 32 ? 32 : 16;          // columns per tcgen05.ld
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-byte alignment
+    const uint32_t sA = smem_base;
+    const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+    const uint32_t bar_full = sB + STAGES * B_STAGE_BYTES;                // STAGES x 8 bytes
+    const uint32_t bar_empty = bar_full + STAGES * 8;
+    const uint32_t bar_tmem = bar_empty + STAGES * 8;
+    const uint32_t tmem_slot = bar_tmem + 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, n_blk = blockIdx.y, phase = blockIdx.z;
+    const int num_kb = p.n_taps * p.c_chunks;
+
+    // tile origin in the virtual output grid
+    int img0, h0;
+    if (p.tile_imgs == 1) { img0 = m_tile / p.tiles_per_img; h0 = (m_tile - img0 * p.tiles_per_img) * p.tile_h; }
+    else { img0 = m_tile * p.tile_imgs; h0 = 0; }
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB);
+        for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tmem, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t par = (uint32_t)((kb / STAGES) & 1);
+                mbar_wait(bar_empty + 8 * s, par ^ 1u);
+                mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+                const int tap = kb / p.c_chunks, cc = kb - tap * p.c_chunks;
+                const int mi = p.tap_map[phase][tap];
+                const CUtensorMap *ma = mi == 0 ? &mapA0 : (mi == 1 ? &mapA1 : (mi == 2 ? &mapA2 : &mapA3));
+                tma_load_4d(sA + s * A_STAGE_BYTES, ma, bar_full + 8 * s, cc * BLOCK_K, (int)p.tap_dw[phase][tap],
+                            h0 + (int)p.tap_dh[phase][tap], img0);
+                tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, bar_full + 8 * s, tap * p.a_c + cc * BLOCK_K,
+                            phase * p.n_total + n_blk * BLOCK_N);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t par = (uint32_t)((kb / STAGES) & 1);
+                mbar_wait(bar_full + 8 * s, par);
+                tc_fence_after();
+                const uint64_t da = umma_desc_sw128(sA + s * A_STAGE_BYTES, 0, 1024);
+                const uint64_t db = umma_desc_sw128(sB + s * B_STAGE_BYTES, 0, 1024);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                    // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
+                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(bar_empty + 8 * s);           // smem stage reusable once these MMAs retire
+            }
+            umma_commit(bar_tmem);                        // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                    // row of the 128-row tile
+        const int per_img = p.tile_h * p.q_w;
+        const int i_img = row / per_img, rem = row - i_img * per_img;
+        const int i_row = rem / p.q_w, i_col = rem - i_row * p.q_w;
+        const int img = img0 + i_img;
+        const bool valid = img < p.a_n;
+        const int oh = (h0 + i_row) * p.out_sh + p.out_oh[phase];
+        const int ow = i_col * p.out_sw + p.out_ow[phase];
+        const size_t pix = ((size_t)img * p.out_h + oh) * p.out_w + ow;
+        const float inv_sigma = p.sigma ? 1.0f / __ldg(p.sigma) : 1.0f;
+
+        mbar_wait(bar_tmem, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+            uint32_t raw[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            if constexpr (CH == 32) tmem_ld_32x32(taddr, raw);
+            else tmem_ld_32x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&raw));
+            tmem_ld_wait();
+            const int n0 = n_blk * BLOCK_N + c0;
+            float v[CH];
+#pragma unroll
+            for (int j = 0; j < CH; j++) v[j] = __uint_as_float(raw[j]) * inv_sigma;
+
+            if (p.epi_mode == IPR_EPI_BIAS_LRELU) {
+#pragma unroll
+                for (int j = 0; j < CH; j++) {
+                    float t = v[j] + (p.bias ? __ldg(p.bias + n0 + j) : 0.0f);
+                    v[j] = t > 0.0f ? t : t * p.slope;
+                }
+            } else if (p.epi_mode == IPR_EPI_MASK) {
+                if (valid) {
+                    const uint4 *mp = reinterpret_cast<const uint4 *>(p.mask + pix * p.out_c + n0);
+#pragma unroll
+                    for (int g = 0; g < CH / 8; g++) {
+                        const uint4 mv = __ldg(mp + g);
+                        const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[h]);
+                            const float2 f2 = __bfloat1622float2(b2);
+                            v[g * 8 + 2 * h] *= f2.x > 0.0f ? 1.0f : p.slope;
+                            v[g * 8 + 2 * h + 1] *= f2.y > 0.0f ? 1.0f : p.slope;
+                        }
+                    }
+                }
+            } else if (p.epi_mode == IPR_EPI_TANH_NCHW) {
+#pragma unroll
+                for (int j = 0; j < CH; j++) v[j] = tanhf(v[j]);
+            }
+
+            if (p.stats) {
+                // per-column sum / sum of squares over this warp's 32 rows: 31-step transposing butterfly
+                float s1[CH], s2[CH];
+#pragma unroll
+                for (int j = 0; j < CH; j++) { const float t = valid ? v[j] : 0.0f; s1[j] = t; s2[j] = t * t; }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+                    if (off < CH) {
+#pragma unroll
+                        for (int i = 0; i < off; i++) {
+                            const float snd1 = up ? s1[i] : s1[i + off], kp1 = up ? s1[i + off] : s1[i];
+                            const float snd2 = up ? s2[i] : s2[i + off], kp2 = up ? s2[i + off] : s2[i];
+                            s1[i] = kp1 + __shfl_xor_sync(0xffffffffu, snd1, off);
+                            s2[i] = kp2 + __shfl_xor_sync(0xffffffffu, snd2, off);
+                        }
+                    } else {   // CH == 16 and off == 16: plain pairwise sum, both halves keep all 16 columns
+#pragma unroll
+                        for (int i = 0; i < CH; i++) {
+                            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+                            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+                        }
+                    }
+                }
+                // lane L now holds column (L mod CH)
+                if (lane < CH) {
+                    const size_t srow = ((size_t)phase * p.m_tiles + m_tile) * 4 + q;
+                    float *dst = p.stats + srow * 2 * p.n_total;
+                    dst[n0 + lane] = s1[0];
+                    dst[p.n_total + n0 + lane] = s2[0];
+                }
+            }
+
+            if (!valid) continue;
+            if (p.epi_mode == IPR_EPI_TANH_NCHW || p.epi_mode == IPR_EPI_LINEAR_NCHW) {
+                float *o = reinterpret_cast<float *>(p.out);
+#pragma unroll
+                for (int j = 0; j < CH; j++) {
+                    const int n = n0 + j;
+                    if (n < p.n_valid) o[(((size_t)img * p.out_c + n) * p.out_h + oh) * p.out_w + ow] = v[j];
+                }
+            } else if (p.epi_mode == IPR_EPI_LINEAR_F32) {
+                float *o = reinterpret_cast<float *>(p.out) + pix * p.out_c + n0;
+#pragma unroll
+                for (int j = 0; j < CH; j++) if (n0 + j < p.n_valid) o[j] = v[j];
+            } else {
+                __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_c + n0;
+                if (n0 + CH <= p.n_valid) {
+#pragma unroll
+                    for (int g = 0; g < CH / 8; g++) {
+                        uint4 pk;
+                        pk.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                        pk.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                        reinterpret_cast<uint4 *>(o)[g] = pk;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CH; j++) if (n0 + j < p.n_valid) o[j] = __float2bfloat16(v[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BLOCK_N, int STAGES>
+int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3 grid, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 2) * 8 + 1024 + 64;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    tapgemm_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], mb, p);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+int tile_geometry(const ipr_tapgemm_t *d, TgParams &p)
+{
+    const int per_img = d->q_h * d->q_w;
+    IPR_REQUIRE(per_img > 0 && d->q_w <= 128, IPR_E_UNSUPPORTED);
+    if (per_img >= BLOCK_M) {
+        IPR_REQUIRE(BLOCK_M % d->q_w == 0, IPR_E_UNSUPPORTED);
+        p.tile_h = BLOCK_M / d->q_w;
+        IPR_REQUIRE(d->q_h % p.tile_h == 0, IPR_E_UNSUPPORTED);
+        p.tile_imgs = 1;
+        p.tiles_per_img = d->q_h / p.tile_h;
+        p.m_tiles = d->a_n * p.tiles_per_img;
+    } else {
+        IPR_REQUIRE(BLOCK_M % per_img == 0, IPR_E_UNSUPPORTED);
+        p.tile_h = d->q_h;
+        p.tile_imgs = BLOCK_M / per_img;
+        p.tiles_per_img = 1;
+        p.m_tiles = (d->a_n + p.tile_imgs - 1) / p.tile_imgs;
+    }
+    return IPR_OK;
+}
+
+}  // namespace
+
+extern "C" int ipr_tapgemm_m_tiles(const ipr_tapgemm_t *d)
+{
+    if (!d) return IPR_E_NULL;
+    TgParams p;
+    int rc = tile_geometry(d, p);
+    return rc != IPR_OK ? rc : p.m_tiles;
+}
+
+extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
+{
+    IPR_REQUIRE(d, IPR_E_NULL);
+    IPR_REQUIRE(d->a && d->b && d->out, IPR_E_NULL);
+    IPR_REQUIRE(d->a_n > 0 && d->a_h > 0 && d->a_w > 0 && d->a_c > 0, IPR_E_SHAPE);
+    IPR_REQUIRE(d->a_c % BLOCK_K == 0, IPR_E_UNSUPPORTED);
+    IPR_REQUIRE(d->n_taps >= 1 && d->n_taps <= IPR_TG_MAX_TAPS && d->n_phases >= 1 && d->n_phases <= IPR_TG_MAX_PHASES,
+                IPR_E_SHAPE);
+    IPR_REQUIRE(d->block_n == 16 || d->block_n == 32 || d->block_n == 64 || d->block_n == 128, IPR_E_UNSUPPORTED);
+    IPR_REQUIRE(d->n_total > 0 && d->n_total % d->block_n == 0, IPR_E_SHAPE);
+    IPR_REQUIRE(ipr_aligned16(d->a) && ipr_aligned16(d->b) && ipr_aligned16(d->out), IPR_E_ALIGN);
+    IPR_REQUIRE(d->epi_mode >= 0 && d->epi_mode <= 5, IPR_E_SHAPE);
+    IPR_REQUIRE(d->epi_mode != IPR_EPI_MASK || (d->mask && ipr_aligned16(d->mask)), IPR_E_NULL);
+    if (d->epi_mode == IPR_EPI_LINEAR || d->epi_mode == IPR_EPI_BIAS_LRELU || d->epi_mode == IPR_EPI_MASK)
+        IPR_REQUIRE(d->out_c % 8 == 0, IPR_E_ALIGN);
+    if (d->a_parity) IPR_REQUIRE(d->a_h % 2 == 0 && d->a_w % 2 == 0 && d->a_c % 8 == 0, IPR_E_UNSUPPORTED);
+
+    TgParams p;
+    int rc = tile_geometry(d, p);
+    if (rc != IPR_OK) return rc;
+    p.a_n = d->a_n; p.q_h = d->q_h; p.q_w = d->q_w;
+    p.a_c = d->a_c; p.c_chunks = d->a_c / BLOCK_K; p.n_taps = d->n_taps; p.n_total = d->n_total;
+    for (int ph = 0; ph < IPR_TG_MAX_PHASES; ph++) {
+        for (int t = 0; t < IPR_TG_MAX_TAPS; t++) {
+            p.tap_map[ph][t] = d->tap_map[ph][t]; p.tap_dh[ph][t] = d->tap_dh[ph][t]; p.tap_dw[ph][t] = d->tap_dw[ph][t];
+            if (ph < d->n_phases && t < d->n_taps)
+                IPR_REQUIRE(d->tap_map[ph][t] >= 0 && d->tap_map[ph][t] < (d->a_parity ? 4 : 1), IPR_E_SHAPE);
+        }
+        p.out_oh[ph] = d->out_oh[ph]; p.out_ow[ph] = d->out_ow[ph];
+    }
+    p.epi_mode = d->epi_mode; p.slope = d->slope; p.sigma = d->sigma; p.bias = d->bias;
+    p.mask = (const __nv_bfloat16 *)d->mask; p.out = d->out;
+    p.out_h = d->out_h; p.out_w = d->out_w; p.out_c = d->out_c; p.out_sh = d->out_sh; p.out_sw = d->out_sw;
+    p.n_valid = d->n_valid > 0 ? d->n_valid : d->n_total; p.stats = d->stats;
+
+    // ---- tensor maps (host-encoded, passed by value as kernel parameters: graph-capturable)
+    CUtensorMap ma[4], mb;
+    const uint64_t C = d->a_c, W = d->a_w, H = d->a_h, N = d->a_n;
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)d->q_w, (uint32_t)p.tile_h, (uint32_t)p.tile_imgs};
+    if (!d->a_parity) {
+        IPR_REQUIRE(d->q_w == d->a_w && d->q_h == d->a_h, IPR_E_SHAPE);
+        const uint64_t dims[4] = {C, W, H, N};
+        const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+        rc = make_tmap_bf16(&ma[0], d->a, 4, dims, str, box);
+        if (rc) return rc;
+        ma[1] = ma[2] = ma[3] = ma[0];
+    } else {
+        IPR_REQUIRE(d->q_w == d->a_w / 2 && d->q_h == d->a_h / 2, IPR_E_SHAPE);
+        const uint64_t dims[4] = {C, W / 2, H / 2, N};
+        const uint64_t str[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
+        for (int ph = 0; ph < 2; ph++)
+            for (int pw = 0; pw < 2; pw++) {
+                const char *base = (const char *)d->a + ((size_t)ph * W + pw) * C * 2;
+                rc = make_tmap_bf16(&ma[ph * 2 + pw], base, 4, dims, str, box);
+                if (rc) return rc;
+            }
+    }
+    {
+        const uint64_t K = (uint64_t)d->n_taps * C;
+        const uint64_t dims[2] = {K, (uint64_t)d->n_phases * d->n_total};
+        const uint64_t str[1] = {K * 2};
+        const uint32_t bbox[2] = {(uint32_t)BLOCK_K, (uint32_t)d->block_n};
+        rc = make_tmap_bf16(&mb, d->b, 2, dims, str, bbox);
+        if (rc) return rc;
+    }
+    dim3 grid((unsigned)p.m_tiles, (unsigned)(d->n_total / d->block_n), (unsigned)d->n_phases);
+    cudaStream_t st = ipr_cu(stream);
+    switch (d->block_n) {
+        case 16:  return launch<16, 4>(ma, mb, p, grid, st);
+        case 32:  return launch<32, 4>(ma, mb, p, grid, st);
+        case 64:  return launch<64, 4>(ma, mb, p, grid, st);
+        default:  return launch<128, 3>(ma, mb, p, grid, st);
+    }
+}

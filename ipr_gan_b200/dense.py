@@ -1,0 +1,169 @@
+"""Dense-layer plans over the tap-GEMM kernel (csrc/gemm_tc.cu): how each convolution / transposed
+convolution / linear layer of the DCGAN networks, and each of their data gradients, is expressed as
+taps (shifted TMA boxes) + a packed bf16 weight matrix.
+
+Activations are NHWC bf16 inside the engine; weights stay fp32 masters in the reference's layouts
+(Conv2d: (O, I, kh, kw); ConvTranspose2d: (I, O, kh, kw); Linear: (O, I)) and are re-packed to bf16
+"[phase][n][tap*C + c]" matrices after every optimizer step.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+MAX_TAPS, MAX_PHASES = 16, 4
+EPI_LINEAR, EPI_BIAS_LRELU, EPI_MASK, EPI_TANH_NCHW, EPI_LINEAR_F32, EPI_LINEAR_NCHW = 0, 1, 2, 3, 4, 5
+
+
+class TapGemm(ctypes.Structure):
+    """ipr_tapgemm_t"""
+    _fields_ = [
+        ("a", ctypes.c_void_p), ("a_n", ctypes.c_int32), ("a_h", ctypes.c_int32), ("a_w", ctypes.c_int32),
+        ("a_c", ctypes.c_int32), ("a_parity", ctypes.c_int32), ("q_h", ctypes.c_int32), ("q_w", ctypes.c_int32),
+        ("b", ctypes.c_void_p), ("n_total", ctypes.c_int32), ("block_n", ctypes.c_int32),
+        ("n_phases", ctypes.c_int32), ("n_taps", ctypes.c_int32),
+        ("tap_map", (ctypes.c_int8 * MAX_TAPS) * MAX_PHASES), ("tap_dh", (ctypes.c_int8 * MAX_TAPS) * MAX_PHASES),
+        ("tap_dw", (ctypes.c_int8 * MAX_TAPS) * MAX_PHASES),
+        ("epi_mode", ctypes.c_int32), ("slope", ctypes.c_float), ("sigma", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("out", ctypes.c_void_p),
+        ("out_h", ctypes.c_int32), ("out_w", ctypes.c_int32), ("out_c", ctypes.c_int32),
+        ("out_sh", ctypes.c_int32), ("out_sw", ctypes.c_int32),
+        ("out_oh", ctypes.c_int8 * MAX_PHASES), ("out_ow", ctypes.c_int8 * MAX_PHASES),
+        ("n_valid", ctypes.c_int32), ("stats", ctypes.c_void_p),
+    ]
+
+
+def _bind():
+    L = lib()
+    if not getattr(L, "_tg_bound", False):
+        L.ipr_tapgemm_bf16.restype = ctypes.c_int
+        L.ipr_tapgemm_bf16.argtypes = [ctypes.POINTER(TapGemm), ctypes.c_void_p]
+        L.ipr_tapgemm_m_tiles.restype = ctypes.c_int
+        L.ipr_tapgemm_m_tiles.argtypes = [ctypes.POINTER(TapGemm)]
+        L._tg_bound = True
+    return L
+
+
+# stride-2, k=4, pad=1: kernel row kh reads input row 2*o + kh - 1 = 2*(o + d) + parity
+_S2 = {0: (1, -1), 1: (0, 0), 2: (1, 0), 3: (0, 1)}          # kh -> (parity, d)
+# k4 s2 p1 transposed conv: output row 2*q + r gathers kernel rows kh at input row q + d
+_T2 = {0: ((1, 0), (3, -1)), 1: ((0, 1), (2, 0))}             # r -> ((kh, d), (kh, d))
+
+
+def pick_block_n(n):
+    for bn in (128, 64, 32, 16):
+        if n % bn == 0:
+            return bn
+    raise ValueError("N must be a multiple of 16, got %d" % n)
+
+
+class Plan(object):
+    """Static description of one tap-GEMM layer: tap tables, phases, output mapping, weight packer."""
+
+    def __init__(self, kind, cin, cout, n_pad=None):
+        self.kind, self.cin, self.cout = kind, cin, cout
+        self.n_total = n_pad or cout
+        self.block_n = pick_block_n(self.n_total)
+        self.a_parity, self.n_phases = 0, 1
+        self.out_s, self.out_o = 1, [(0, 0)] * 4
+        k = kind
+        if k in ("conv3", "conv3_dgrad", "convT3"):
+            # conv3: in row = o + kh - 1; the other two: in row = o + 1 - kh
+            flip = k != "conv3"
+            self.taps = [[(0, (1 - kh) if flip else (kh - 1), (1 - kw) if flip else (kw - 1), kh, kw)
+                          for kh in range(3) for kw in range(3)]]
+        elif k in ("conv4s2", "convT4s2_dgrad"):
+            self.a_parity = 1
+            self.taps = [[(2 * _S2[kh][0] + _S2[kw][0], _S2[kh][1], _S2[kw][1], kh, kw)
+                          for kh in range(4) for kw in range(4)]]
+        elif k in ("convT4s2", "conv4s2_dgrad"):
+            self.n_phases, self.out_s = 4, 2
+            self.taps, self.out_o = [], []
+            for rh in range(2):
+                for rw in range(2):
+                    self.taps.append([(0, dh, dw, kh, kw) for (kh, dh) in _T2[rh] for (kw, dw) in _T2[rw]])
+                    self.out_o.append((rh, rw))
+        elif k == "linear":
+            self.taps = [[(0, 0, 0, 0, 0)]]
+        else:
+            raise ValueError(kind)
+        self.n_taps = len(self.taps[0])
+
+    # weight (fp32, reference layout) -> bf16 [phase][n_total][taps*cin]
+    def pack(self, w, perm=None):
+        k = self.kind
+        if k == "linear":
+            m = w if perm is None else w[perm]
+            mats = [m]                                               # (N, K)
+        else:
+            mats = []
+            for taps in self.taps:
+                cols = []
+                for (_, _, _, kh, kw) in taps:
+                    if k in ("conv3", "conv4s2"):                    # Conv2d weight (O, I, kh, kw): n = O, c = I
+                        cols.append(w[:, :, kh, kw])
+                    elif k in ("conv3_dgrad", "conv4s2_dgrad"):      # n = I, c = O
+                        cols.append(w[:, :, kh, kw].t())
+                    elif k in ("convT3", "convT4s2"):                # ConvT weight (I, O, kh, kw): n = O, c = I
+                        cols.append(w[:, :, kh, kw].t())
+                    else:                                            # convT4s2_dgrad: n = I, c = O
+                        cols.append(w[:, :, kh, kw])
+                mats.append(torch.cat(cols, dim=1))
+        out = torch.zeros(self.n_phases, self.n_total, mats[0].shape[1], device=w.device, dtype=torch.bfloat16)
+        for i, m in enumerate(mats):
+            out[i, :m.shape[0]] = m.to(torch.bfloat16)
+        return out.contiguous()
+
+    def out_hw(self, a_h, a_w):
+        if self.kind in ("conv4s2", "convT4s2_dgrad"):
+            return a_h // 2, a_w // 2
+        if self.kind in ("convT4s2", "conv4s2_dgrad"):
+            return a_h * 2, a_w * 2
+        return a_h, a_w
+
+    def run(self, a, b_packed, epi=EPI_LINEAR, slope=0.0, sigma=None, bias=None, mask=None, out=None,
+            want_stats=False, n_valid=None, out_nchw_c=None):
+        """a: (N, H, W, C) bf16 NHWC.  Returns (out, stats or None)."""
+        L = _bind()
+        assert a.dtype == torch.bfloat16 and a.is_cuda and a.is_contiguous() and a.dim() == 4
+        N, H, W, C = a.shape
+        assert C == self.cin, (C, self.cin)
+        oh, ow = self.out_hw(H, W)
+        d = TapGemm()
+        d.a, d.a_n, d.a_h, d.a_w, d.a_c = a.data_ptr(), N, H, W, C
+        d.a_parity = self.a_parity
+        d.q_h, d.q_w = (H // 2, W // 2) if self.a_parity else (H, W)
+        d.b, d.n_total, d.block_n = b_packed.data_ptr(), self.n_total, self.block_n
+        d.n_phases, d.n_taps = self.n_phases, self.n_taps
+        for ph, taps in enumerate(self.taps):
+            for t, (mp, dh, dw, _, _) in enumerate(taps):
+                d.tap_map[ph][t], d.tap_dh[ph][t], d.tap_dw[ph][t] = mp, dh, dw
+            d.out_oh[ph], d.out_ow[ph] = self.out_o[ph]
+        d.epi_mode, d.slope = epi, float(slope)
+        d.sigma = sigma.data_ptr() if sigma is not None else None
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.mask = mask.data_ptr() if mask is not None else None
+        nv = n_valid or self.cout
+        if out is None:
+            if epi in (EPI_TANH_NCHW, EPI_LINEAR_NCHW):
+                out = torch.empty(N, nv, oh, ow, device=a.device, dtype=torch.float32)
+            elif epi == EPI_LINEAR_F32:
+                out = torch.empty(N, oh, ow, nv, device=a.device, dtype=torch.float32)
+            else:
+                out = torch.empty(N, oh, ow, nv, device=a.device, dtype=torch.bfloat16)
+        d.out, d.out_h, d.out_w = out.data_ptr(), oh, ow
+        d.out_c = out.shape[1] if epi in (EPI_TANH_NCHW, EPI_LINEAR_NCHW) else out.shape[3]
+        d.out_sh = d.out_sw = self.out_s
+        d.n_valid = nv
+        stats = None
+        if want_stats:
+            tiles = L.ipr_tapgemm_m_tiles(ctypes.byref(d))
+            if tiles < 0:
+                check(tiles, "ipr_tapgemm_m_tiles")
+            stats = torch.empty(tiles * self.n_phases * 4, 2, self.n_total, device=a.device, dtype=torch.float32)
+            d.stats = stats.data_ptr()
+        check(L.ipr_tapgemm_bf16(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              "ipr_tapgemm_bf16(%s)" % self.kind)
+        return out, stats
