@@ -204,6 +204,37 @@ typedef struct {
 int ipr_tapgemm_m_tiles(const ipr_tapgemm_t *d_host);
 int ipr_tapgemm_bf16(const ipr_tapgemm_t *d_host, ipr_stream_t stream);
 
+/* Weight gradient of a tap-GEMM layer (tcgen05, MN-major operands, split-K over pixels):
+ *     ws[split][p][n][t*x_c + c] = sum_{pixels m in the split} Y[pix_y(m)][n] * X[pix(m) + tap_t][c]
+ * Y is the output-gradient-like operand (n = rows of dW), X the activation-like operand read with the
+ * layer's taps.  y_parity / x_parity = 1: that tensor has twice the resolution of the (q_h, q_w) pixel
+ * grid and is addressed through parity sub-grids (y_map[p] for Y; tap_map[p][t] for X).
+ * Replaces the weight-gradient halves of cudnn convolution_backward / addmm backward under
+ * networks/conv_generator.py and networks/sn_discriminator.py. */
+typedef struct {
+    const void *y; int32_t y_c, y_parity;
+    const void *x; int32_t x_c, x_parity;
+    int32_t n_imgs, q_h, q_w;
+    int32_t n_phases, n_taps;
+    int8_t  y_map[IPR_TG_MAX_PHASES];
+    int8_t  tap_map[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
+    int8_t  tap_dh[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
+    int8_t  tap_dw[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
+    float  *workspace;             /* ipr_wgrad_workspace_bytes() */
+    int32_t splits;
+} ipr_wgrad_t;
+
+size_t ipr_wgrad_workspace_bytes(const ipr_wgrad_t *d_host);
+int    ipr_wgrad_total_kblocks(const ipr_wgrad_t *d_host);     /* 64-pixel blocks of the reduction */
+int    ipr_wgrad_bf16(const ipr_wgrad_t *d_host, ipr_stream_t stream);
+
+/* grad[row(n)*s_n + col_off[p][k]] (+)= scale * sum_splits ws[split][p][n][k]   (col_off < 0: skipped;
+ * row(n) = row_map ? row_map[n] : n).  Adds the splits in a fixed order and scatters from the GEMM layout
+ * into the parameter's own layout ((O,I,kh,kw), (I,O,kh,kw) or (O,I)). */
+int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_rows, int k_total,
+                         const int32_t *col_off, const int32_t *row_map, int64_t s_n, float *grad,
+                         int accumulate, float scale, ipr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -167,3 +167,104 @@ class Plan(object):
         check(L.ipr_tapgemm_bf16(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
               "ipr_tapgemm_bf16(%s)" % self.kind)
         return out, stats
+
+
+class WGrad(ctypes.Structure):
+    """ipr_wgrad_t"""
+    _fields_ = [
+        ("y", ctypes.c_void_p), ("y_c", ctypes.c_int32), ("y_parity", ctypes.c_int32),
+        ("x", ctypes.c_void_p), ("x_c", ctypes.c_int32), ("x_parity", ctypes.c_int32),
+        ("n_imgs", ctypes.c_int32), ("q_h", ctypes.c_int32), ("q_w", ctypes.c_int32),
+        ("n_phases", ctypes.c_int32), ("n_taps", ctypes.c_int32),
+        ("y_map", ctypes.c_int8 * MAX_PHASES),
+        ("tap_map", (ctypes.c_int8 * MAX_TAPS) * MAX_PHASES), ("tap_dh", (ctypes.c_int8 * MAX_TAPS) * MAX_PHASES),
+        ("tap_dw", (ctypes.c_int8 * MAX_TAPS) * MAX_PHASES),
+        ("workspace", ctypes.c_void_p), ("splits", ctypes.c_int32),
+    ]
+
+
+_SM_COUNT = 148
+
+
+class WGradPlan(object):
+    """Weight gradient of the layer described by a forward Plan (conv3 / conv4s2 / convT4s2 / linear).
+
+    ``y`` is the gradient w.r.t. the layer output (NHWC bf16), ``x`` the layer input (NHWC bf16); the result
+    is written into ``grad`` which has the parameter's own fp32 layout."""
+
+    def __init__(self, fwd, weight_shape, row_perm=None, col_off=None, s_n=None):
+        self.fwd = fwd
+        k = fwd.kind
+        assert k in ("conv3", "conv4s2", "convT4s2", "linear"), k
+        self.y_parity = 1 if k == "convT4s2" else 0
+        self.x_parity = fwd.a_parity
+        self.n_phases, self.n_taps = fwd.n_phases, fwd.n_taps
+        self.rows = fwd.cout                      # rows of dW in GEMM layout (n)
+        self.x_c = fwd.cin
+        self.k_total = self.n_taps * self.x_c
+        self.row_perm = row_perm
+        if col_off is None:
+            col_off = torch.full((self.n_phases, self.k_total), -1, dtype=torch.int32)
+            if k == "linear":
+                col_off[0] = torch.arange(self.k_total, dtype=torch.int32)
+                s_n = weight_shape[1]
+            else:
+                ksz = weight_shape[-1]
+                c = torch.arange(self.x_c, dtype=torch.int32)
+                for ph, taps in enumerate(fwd.taps):
+                    for t, (_, _, _, kh, kw) in enumerate(taps):
+                        if k == "convT4s2":        # (I, O, kh, kw): n = O (stride k*k), c = I (stride O*k*k)
+                            col_off[ph, t * self.x_c:(t + 1) * self.x_c] = c * (weight_shape[1] * ksz * ksz) + kh * ksz + kw
+                        else:                      # (O, I, kh, kw): n = O (stride I*k*k), c = I (stride k*k)
+                            col_off[ph, t * self.x_c:(t + 1) * self.x_c] = c * (ksz * ksz) + kh * ksz + kw
+                s_n = ksz * ksz if k == "convT4s2" else weight_shape[1] * ksz * ksz
+        self.col_off_host, self.s_n = col_off.contiguous(), int(s_n)
+        self._dev = {}
+
+    def _tables(self, device):
+        key = str(device)
+        if key not in self._dev:
+            rp = self.row_perm.to(device=device, dtype=torch.int32).contiguous() if self.row_perm is not None else None
+            self._dev[key] = (self.col_off_host.to(device), rp)
+        return self._dev[key]
+
+    def run(self, y, x, grad, accumulate=False, scale=1.0, splits=None):
+        L = _bind()
+        if not getattr(L, "_wg_bound", False):
+            L.ipr_wgrad_bf16.argtypes = [ctypes.POINTER(WGrad), ctypes.c_void_p]
+            L.ipr_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(WGrad)]
+            L.ipr_wgrad_total_kblocks.argtypes = [ctypes.POINTER(WGrad)]
+            L._wg_bound = True
+        assert y.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and y.is_contiguous() and x.is_contiguous()
+        assert grad.dtype == torch.float32 and grad.is_contiguous()
+        N, xh, xw, xc = x.shape
+        assert xc == self.x_c and y.shape[3] == self.rows, (x.shape, y.shape, self.x_c, self.rows)
+        d = WGrad()
+        d.y, d.y_c, d.y_parity = y.data_ptr(), y.shape[3], self.y_parity
+        d.x, d.x_c, d.x_parity = x.data_ptr(), xc, self.x_parity
+        d.n_imgs = N
+        d.q_h, d.q_w = (xh // 2, xw // 2) if self.x_parity else (xh, xw)
+        d.n_phases, d.n_taps = self.n_phases, self.n_taps
+        for ph, taps in enumerate(self.fwd.taps):
+            for t, (mp, dh, dw, _, _) in enumerate(taps):
+                d.tap_map[ph][t], d.tap_dh[ph][t], d.tap_dw[ph][t] = mp, dh, dw
+            d.y_map[ph] = (2 * self.fwd.out_o[ph][0] + self.fwd.out_o[ph][1]) if self.y_parity else 0
+        kblocks = L.ipr_wgrad_total_kblocks(ctypes.byref(d))
+        if kblocks < 0:
+            check(kblocks, "ipr_wgrad_total_kblocks")
+        if splits is None:
+            n_units = self.n_taps * (xc // 64)
+            ctas = ((self.rows + 127) // 128) * ((n_units + 1) // 2) * self.n_phases
+            splits = max(1, min(kblocks // 4 if kblocks >= 8 else 1, (3 * _SM_COUNT + ctas - 1) // ctas, 64))
+        d.splits = splits
+        nbytes = L.ipr_wgrad_workspace_bytes(ctypes.byref(d))
+        ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+        d.workspace = ws.data_ptr()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(L.ipr_wgrad_bf16(ctypes.byref(d), st), "ipr_wgrad_bf16(%s)" % self.fwd.kind)
+        col_off, row_map = self._tables(x.device)
+        check(L.ipr_wgrad_reduce_f32(ws.data_ptr(), splits, self.n_phases, self.rows, self.k_total,
+                                     col_off.data_ptr(), row_map.data_ptr() if row_map is not None else None,
+                                     self.s_n, grad.data_ptr(), int(bool(accumulate)), float(scale), st),
+              "ipr_wgrad_reduce_f32")
+        return grad

@@ -111,3 +111,38 @@ def test_data_gradients(kind, B, C, O, H):
     out, _ = plan.run(nhwc(dy), plan.pack(w), epi=dense.EPI_MASK, slope=0.1, mask=mask)
     want = x.grad * torch.where(mask.float() > 0, 1.0, 0.1).permute(0, 3, 1, 2)
     close(out.permute(0, 3, 1, 2), want)
+
+
+@pytest.mark.parametrize("kind,B,C,O,H", [("conv3", 8, 64, 128, 16), ("conv3", 4, 256, 512, 4), ("conv4s2", 8, 64, 64, 32),
+                                          ("conv4s2", 16, 256, 256, 8), ("convT4s2", 8, 512, 256, 4),
+                                          ("convT4s2", 4, 128, 64, 16), ("linear", 200, 128, 8192, 1)])
+def test_weight_gradients(kind, B, C, O, H):
+    """tcgen05 wgrad (MN-major operands, split-K) against autograd of the fp32 op on bf16-rounded operands."""
+    from ipr_gan_b200 import dense
+    torch.manual_seed(4)
+    if kind == "linear":
+        w = (torch.randn(O, C, device="cuda") * 0.05).requires_grad_(True)
+        x = torch.randn(B, C, device="cuda")
+        y = bf(x) @ w.t()
+        xa = x.to(torch.bfloat16).view(B, 1, 1, C)
+    else:
+        ksz = 3 if kind == "conv3" else 4
+        if kind == "convT4s2":
+            w = (torch.randn(C, O, ksz, ksz, device="cuda") * 0.05).requires_grad_(True)
+            x = torch.randn(B, C, H, H, device="cuda")
+            y = F.conv_transpose2d(bf(x), w, stride=2, padding=1)
+        else:
+            w = (torch.randn(O, C, ksz, ksz, device="cuda") * 0.05).requires_grad_(True)
+            x = torch.randn(B, C, H, H, device="cuda")
+            y = F.conv2d(bf(x), w, stride=1 if kind == "conv3" else 2, padding=1)
+        xa = nhwc(x)
+    dy = torch.randn_like(y)
+    y.backward(bf(dy))
+    plan = dense.Plan(kind, C, O)
+    wg = dense.WGradPlan(plan, tuple(w.shape))
+    dya = dy.to(torch.bfloat16).view(B, 1, 1, O) if kind == "linear" else nhwc(dy)
+    grad = torch.full_like(w, 7.0).detach()
+    wg.run(dya, xa, grad)
+    close(grad, w.grad, tol=5e-3)
+    wg.run(dya, xa, grad, accumulate=True, scale=0.5, splits=3)
+    close(grad, 1.5 * w.grad, tol=5e-3)
