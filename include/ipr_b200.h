@@ -235,6 +235,47 @@ int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_r
                          const int32_t *col_off, const int32_t *row_map, int64_t s_n, float *grad,
                          int accumulate, float scale, ipr_stream_t stream);
 
+/* ------------------------------------------------------------------ memory-bound layers around the GEMMs */
+
+/* out[(n,h,w)][k] (bf16, 64 columns) = x[n, c, h+kh-1, w+kw-1] for k = (kh*3+kw)*3 + c < 27, else 0;
+ * x: (batch, 3, H, W) fp32 NCHW.  tanh_out (optional, same shape): x is multiplied by (1 - tanh_out^2)
+ * (Tanh backward of networks/conv_generator.py:22 fused into the gather).  Feeds the first discriminator
+ * convolution (networks/sn_discriminator.py:15, Cin = 3) and the last generator layer's gradients. */
+int ipr_im2col3_bf16(const float *x, const float *tanh_out, void *out, int64_t batch, int height, int width,
+                     ipr_stream_t stream);
+
+/* BatchNorm2d training-mode statistics (networks/conv_generator.py:9): partial = [rows][2][C] column sums and
+ * sums of squares produced by the GEMM epilogue; count = elements per channel.  Writes scale = gamma*rstd,
+ * shift = beta - mean*scale, mean, rstd and (if running_mean != NULL) updates the running statistics with
+ * `momentum` and the unbiased variance; num_batches_tracked (optional) += 1.  running_* = NULL reproduces
+ * DisableBatchNormStats (models/util.py:55-69). */
+int ipr_bn_finalize_f32(const float *partial, int rows, int channels, double count, float eps, float momentum,
+                        const float *gamma, const float *beta, float *running_mean, float *running_var,
+                        int64_t *num_batches_tracked, float *scale, float *shift, float *mean, float *rstd,
+                        ipr_stream_t stream);
+
+/* y = relu(x*scale[c] + shift[c]); x, y: [rows][C] bf16 (NHWC). */
+int ipr_bn_apply_relu_bf16(const void *x, void *y, const float *scale, const float *shift, int64_t rows,
+                           int channels, ipr_stream_t stream);
+
+size_t ipr_bn_bwd_workspace_bytes(int channels);
+/* Backward of relu(batchnorm(xraw)) in training mode.  dy, xraw, act (= the forward output, used as ReLU mask),
+ * dx: [rows][C] bf16.  dgamma / dbeta are written or accumulated.  If sign != NULL the white-box sign-loss
+ * gradient  -sign_scale * sign_c / C  (where gamma0 - gamma_c*sign_c > 0) is added to dgamma
+ * (tools/sign_model.py:48): the sign loss costs no extra pass. */
+int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const void *act, const float *gamma, const float *mean,
+                         const float *rstd, void *dx, float *dgamma, float *dbeta, int accumulate,
+                         const float *sign, float gamma0, float sign_scale, void *workspace, size_t workspace_bytes,
+                         int64_t rows, int channels, ipr_stream_t stream);
+
+/* Final Linear(K -> 1) of the discriminator (networks/sn_discriminator.py:21): logits[b] = a[b,:].w / sigma + bias.
+ * a: [batch][K] bf16, w: fp32 [K] in the activation's (NHWC) feature order. */
+int ipr_dfc_fwd_bf16(const void *a, const float *w, const float *sigma, const float *bias, float *logits,
+                     int batch, int k, ipr_stream_t stream);
+/* da[b,k] = dlogit[b]*w[k]/sigma * (a[b,k] > 0 ? 1 : slope)   (bf16);  dw[k] (+)= sum_b dlogit[b]*a[b,k] (optional). */
+int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigma, const float *dlogit, void *da, float *dw,
+                     int accumulate_dw, float slope, int batch, int k, ipr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

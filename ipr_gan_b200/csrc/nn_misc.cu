@@ -1,0 +1,403 @@
+// nn_misc.cu -- the memory-bound layers around the tensor-core GEMMs of the DCGAN step:
+//   * im2col3: 3-channel NCHW fp32 image (optionally times tanh') -> [pixel][64] bf16 patch matrix
+//     (K = 27 is far too thin for an implicit GEMM; one 128-byte row per pixel feeds the tap GEMM);
+//   * BatchNorm (training mode): statistics finalisation from the GEMM epilogue's column partials,
+//     fused scale/shift + ReLU, and the two-pass backward with the ReLU mask and the white-box
+//     sign-loss gradient folded into d(gamma) (tools/sign_model.py:48 -> zero extra passes);
+//   * the discriminator's final Linear(8192 -> 1): GEMV forward, and backward fused with LeakyReLU'.
+// All bf16 tensors are NHWC; vector width 8 bf16 (16 bytes) per thread.
+#include "ipr_common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[i]));
+        f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t *>(&t);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------------------------ im2col3
+// out[(n,h,w)][k], k = (kh*3+kw)*3 + c  <-  x[n, c, h+kh-1, w+kw-1] (zero outside), k in [27,64) = 0.
+// With `t` given (tanh output), the source value is x * (1 - t^2): the Tanh backward of the generator's
+// last layer fused into the gather.
+__global__ void __launch_bounds__(256)
+im2col3_kernel(const float *__restrict__ x, const float *__restrict__ t, uint4 *__restrict__ out,
+               long long pixels, int H, int W)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const size_t plane = (size_t)H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += stride) {
+        const int w = (int)(p % W);
+        const long long r = p / W;
+        const int h = (int)(r % H);
+        const long long n = r / H;
+        float v[32];
+#pragma unroll
+        for (int k = 27; k < 32; k++) v[k] = 0.0f;
+#pragma unroll
+        for (int kh = 0; kh < 3; kh++)
+#pragma unroll
+            for (int kw = 0; kw < 3; kw++) {
+                const int hh = h + kh - 1, ww = w + kw - 1;
+                const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float val = 0.0f;
+                    if (ok) {
+                        const size_t idx = ((size_t)n * 3 + c) * plane + (size_t)hh * W + ww;
+                        val = __ldg(x + idx);
+                        if (t) { const float tv = __ldg(t + idx); val *= (1.0f - tv * tv); }
+                    }
+                    v[(kh * 3 + kw) * 3 + c] = val;
+                }
+            }
+        uint4 *dst = out + p * 8;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = v[g * 8 + i];
+            dst[g] = pack8(f);
+        }
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int g = 4; g < 8; g++) dst[g] = z;
+    }
+}
+
+// ------------------------------------------------------------------------------------ BatchNorm forward
+// partial: [rows][2][C] column sums / sums of squares.  One warp-column per channel group; double accumulation.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float *__restrict__ partial, int rows, int C, double count, float eps, float momentum,
+                   const float *__restrict__ gamma, const float *__restrict__ beta,
+                   float *__restrict__ running_mean, float *__restrict__ running_var, long long *__restrict__ num_batches,
+                   float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ mean_out,
+                   float *__restrict__ rstd_out)
+{
+    __shared__ double s1[8][33], s2[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double a = 0.0, b = 0.0;
+    if (c < C)
+        for (int r = threadIdx.y; r < rows; r += 8) {
+            a += (double)partial[(size_t)r * 2 * C + c];
+            b += (double)partial[(size_t)r * 2 * C + C + c];
+        }
+    s1[threadIdx.y][threadIdx.x] = a; s2[threadIdx.y][threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        for (int y = 1; y < 8; y++) { a += s1[y][threadIdx.x]; b += s2[y][threadIdx.x]; }
+        const double mean = a / count;
+        double var = b / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float g = gamma[c], be = beta[c];
+        scale[c] = g * rstd;
+        shift[c] = be - (float)mean * g * rstd;
+        mean_out[c] = (float)mean;
+        rstd_out[c] = rstd;
+        if (running_mean) {
+            const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+            running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+    }
+    if (num_batches && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *num_batches += 1;
+}
+
+// y = relu(x * scale[c] + shift[c]) over [rows][C] bf16
+__global__ void __launch_bounds__(256)
+bn_apply_relu_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, const float *__restrict__ scale,
+                     const float *__restrict__ shift, long long n_vec, int c_vec)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const int c0 = (int)(i % c_vec) * 8;
+        float f[8];
+        unpack8(__ldg(x + i), f);
+#pragma unroll
+        for (int k = 0; k < 8; k++) f[k] = fmaxf(fmaf(f[k], __ldg(scale + c0 + k), __ldg(shift + c0 + k)), 0.0f);
+        y[i] = pack8(f);
+    }
+}
+
+// ------------------------------------------------------------------------------------ BatchNorm backward
+// pass 1: per-CTA partial sums over a slab of rows of  g = dy * (act > 0)  and  g * xhat.
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xraw, const uint4 *__restrict__ act,
+                     const float *__restrict__ mean, const float *__restrict__ rstd, long long rows, int c_vec,
+                     float *__restrict__ partial)
+{
+    extern __shared__ float sm[];                    // [ry][2][C]
+    const int C = c_vec * 8;
+    const int ry_n = blockDim.x / c_vec;
+    const int cv = threadIdx.x % c_vec, ry = threadIdx.x / c_vec;
+    float sg[8], sx[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sg[k] = sx[k] = 0.0f;
+    if (ry < ry_n) {
+        float mu[8], rs[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { mu[k] = mean[cv * 8 + k]; rs[k] = rstd[cv * 8 + k]; }
+        for (long long r = (long long)blockIdx.x * ry_n + ry; r < rows; r += (long long)gridDim.x * ry_n) {
+            float d[8], xv[8], av[8];
+            unpack8(__ldg(dy + r * c_vec + cv), d);
+            unpack8(__ldg(xraw + r * c_vec + cv), xv);
+            unpack8(__ldg(act + r * c_vec + cv), av);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float g = av[k] > 0.0f ? d[k] : 0.0f;
+                sg[k] += g;
+                sx[k] += g * (xv[k] - mu[k]) * rs[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { sm[(ry * 2) * C + cv * 8 + k] = sg[k]; sm[(ry * 2 + 1) * C + cv * 8 + k] = sx[k]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float acc = 0.0f;
+        for (int y = 0; y < ry_n; y++) acc += sm[y * 2 * C + i];
+        partial[(size_t)blockIdx.x * 2 * C + i] = acc;
+    }
+}
+
+// pass 1b: dbeta, dgamma (+ sign-loss gradient) and the per-channel coefficients of pass 2.
+//   dx = a[c] * g + b[c] * xraw + d[c]   with  a = gamma*rstd,  b = -gamma*rstd^2*dgamma_bn/M,
+//   d = -a*dbeta/M - b*mean
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float *__restrict__ partial, int rows, int C, double count,
+                       const float *__restrict__ gamma, const float *__restrict__ mean, const float *__restrict__ rstd,
+                       float *__restrict__ dgamma, float *__restrict__ dbeta, int accumulate,
+                       const float *__restrict__ sign, float gamma0, float sign_scale,
+                       float *__restrict__ coef)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double sg = 0.0, sx = 0.0;
+    for (int r = 0; r < rows; r++) { sg += (double)partial[(size_t)r * 2 * C + c]; sx += (double)partial[(size_t)r * 2 * C + C + c]; }
+    const float g = gamma[c], rs = rstd[c], mu = mean[c];
+    float dg = (float)sx;
+    const float a = g * rs;
+    const float b = -g * rs * rs * (float)(sx / count);
+    coef[c] = a;
+    coef[C + c] = b;
+    coef[2 * C + c] = -a * (float)(sg / count) - b * mu;
+    if (sign) {                                      // d/dgamma of mean_c relu(gamma0 - gamma*sign)
+        const float s = sign[c];
+        if (gamma0 - g * s > 0.0f) dg += -s * sign_scale / (float)C;
+    }
+    dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+    dbeta[c] = accumulate ? dbeta[c] + (float)sg : (float)sg;
+}
+
+// pass 2: dx = a*g + b*xraw + d
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xraw, const uint4 *__restrict__ act,
+                    const float *__restrict__ coef, uint4 *__restrict__ dx, long long n_vec, int c_vec)
+{
+    const int C = c_vec * 8;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const int c0 = (int)(i % c_vec) * 8;
+        float d[8], xv[8], av[8], o[8];
+        unpack8(__ldg(dy + i), d);
+        unpack8(__ldg(xraw + i), xv);
+        unpack8(__ldg(act + i), av);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float g = av[k] > 0.0f ? d[k] : 0.0f;
+            o[k] = __ldg(coef + c0 + k) * g + __ldg(coef + C + c0 + k) * xv[k] + __ldg(coef + 2 * C + c0 + k);
+        }
+        dx[i] = pack8(o);
+    }
+}
+
+// ------------------------------------------------------------------------------------ final Linear(K -> 1)
+// logits[b] = dot(a[b,:], w) / sigma + bias          one warp per sample
+__global__ void __launch_bounds__(256)
+dfc_fwd_kernel(const uint4 *__restrict__ a, const float *__restrict__ w, const float *__restrict__ sigma,
+               const float *__restrict__ bias, float *__restrict__ logits, int batch, int k_vec)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= batch) return;
+    float acc = 0.0f;
+    for (int i = lane; i < k_vec; i += 32) {
+        float f[8];
+        unpack8(__ldg(a + (size_t)warp * k_vec + i), f);
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(w) + 2 * i), w1 = __ldg(reinterpret_cast<const float4 *>(w) + 2 * i + 1);
+        acc += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z + f[7] * w1.w;
+    }
+    acc = ipr_warp_sum(acc);
+    if (lane == 0) logits[warp] = acc / (sigma ? *sigma : 1.0f) + (bias ? *bias : 0.0f);
+}
+
+// da[b,k] = dlogit[b] * w[k] / sigma * lrelu'(a[b,k])      (gradient w.r.t. the previous conv's pre-activation)
+__global__ void __launch_bounds__(256)
+dfc_bwd_data_kernel(const uint4 *__restrict__ a, const float *__restrict__ w, const float *__restrict__ sigma,
+                    const float *__restrict__ dlogit, uint4 *__restrict__ da, long long n_vec, int k_vec, float slope)
+{
+    const float inv = 1.0f / (sigma ? *sigma : 1.0f);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const int kv = (int)(i % k_vec);
+        const long long b = i / k_vec;
+        const float dl = __ldg(dlogit + b) * inv;
+        float f[8], o[8];
+        unpack8(__ldg(a + i), f);
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(w) + 2 * kv), w1 = __ldg(reinterpret_cast<const float4 *>(w) + 2 * kv + 1);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = dl * wv[k] * (f[k] > 0.0f ? 1.0f : slope);
+        da[i] = pack8(o);
+    }
+}
+
+// dw[k] (+)= sum_b dlogit[b] * a[b,k]   (w.r.t. the normalised weight);  one thread per k, fixed order over b
+__global__ void __launch_bounds__(256)
+dfc_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ dlogit, float *__restrict__ dw,
+                      int batch, int K, int accumulate)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    float acc = 0.0f;
+    for (int b = 0; b < batch; b++) acc += __ldg(dlogit + b) * __bfloat162float(a[(size_t)b * K + k]);
+    dw[k] = accumulate ? dw[k] + acc : acc;
+}
+
+inline unsigned grid_1d(long long items, int threads, int waves = 8) {
+    long long blocks = (items + threads - 1) / threads;
+    const long long cap = (long long)ipr_sm_count() * waves;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+
+extern "C" int ipr_im2col3_bf16(const float *x, const float *tanh_out, void *out, int64_t batch, int height,
+                                int width, ipr_stream_t stream)
+{
+    IPR_REQUIRE(x && out, IPR_E_NULL);
+    IPR_REQUIRE(batch > 0 && height > 0 && width > 0, IPR_E_SHAPE);
+    IPR_REQUIRE(ipr_aligned16(out), IPR_E_ALIGN);
+    const long long pixels = (long long)batch * height * width;
+    im2col3_kernel<<<grid_1d(pixels, 256), 256, 0, ipr_cu(stream)>>>(x, tanh_out, (uint4 *)out, pixels, height, width);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" int ipr_bn_finalize_f32(const float *partial, int rows, int channels, double count, float eps,
+                                   float momentum, const float *gamma, const float *beta, float *running_mean,
+                                   float *running_var, int64_t *num_batches_tracked, float *scale, float *shift,
+                                   float *mean, float *rstd, ipr_stream_t stream)
+{
+    IPR_REQUIRE(partial && gamma && beta && scale && shift && mean && rstd, IPR_E_NULL);
+    IPR_REQUIRE(rows > 0 && channels > 0 && count > 0, IPR_E_SHAPE);
+    dim3 block(32, 8);
+    bn_finalize_kernel<<<(channels + 31) / 32, block, 0, ipr_cu(stream)>>>(
+        partial, rows, channels, count, eps, momentum, gamma, beta, running_mean, running_var,
+        (long long *)num_batches_tracked, scale, shift, mean, rstd);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" int ipr_bn_apply_relu_bf16(const void *x, void *y, const float *scale, const float *shift,
+                                      int64_t rows, int channels, ipr_stream_t stream)
+{
+    IPR_REQUIRE(x && y && scale && shift, IPR_E_NULL);
+    IPR_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0, IPR_E_SHAPE);
+    IPR_REQUIRE(ipr_aligned16(x) && ipr_aligned16(y), IPR_E_ALIGN);
+    const long long n_vec = (long long)rows * channels / 8;
+    bn_apply_relu_kernel<<<grid_1d(n_vec, 256), 256, 0, ipr_cu(stream)>>>((const uint4 *)x, (uint4 *)y, scale, shift,
+                                                                        n_vec, channels / 8);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" size_t ipr_bn_bwd_workspace_bytes(int channels)
+{
+    // partial sums [ctas][2][C] + coefficients [3][C]
+    return ((size_t)ipr_sm_count() * 2 * 2 * channels + 3 * (size_t)channels) * sizeof(float);
+}
+
+extern "C" int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const void *act, const float *gamma,
+                                    const float *mean, const float *rstd, void *dx, float *dgamma, float *dbeta,
+                                    int accumulate, const float *sign, float gamma0, float sign_scale,
+                                    void *workspace, size_t workspace_bytes, int64_t rows, int channels,
+                                    ipr_stream_t stream)
+{
+    IPR_REQUIRE(dy && xraw && act && gamma && mean && rstd && dx && dgamma && dbeta && workspace, IPR_E_NULL);
+    IPR_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0 && channels <= 2048, IPR_E_SHAPE);
+    IPR_REQUIRE(workspace_bytes >= ipr_bn_bwd_workspace_bytes(channels), IPR_E_WORKSPACE);
+    IPR_REQUIRE(ipr_aligned16(dy) && ipr_aligned16(xraw) && ipr_aligned16(act) && ipr_aligned16(dx), IPR_E_ALIGN);
+    const int c_vec = channels / 8;
+    IPR_REQUIRE(c_vec <= 256, IPR_E_UNSUPPORTED);
+    const int ry_n = 256 / c_vec;
+    long long ctas = (rows + ry_n - 1) / ry_n;
+    const long long cap = (long long)ipr_sm_count() * 2;
+    if (ctas > cap) ctas = cap;
+    float *partial = (float *)workspace;
+    float *coef = partial + (size_t)ipr_sm_count() * 2 * 2 * channels;
+    cudaStream_t st = ipr_cu(stream);
+    const size_t smem = (size_t)ry_n * 2 * channels * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    bn_bwd_reduce_kernel<<<(unsigned)ctas, 256, smem, st>>>((const uint4 *)dy, (const uint4 *)xraw, (const uint4 *)act,
+                                                            mean, rstd, rows, c_vec, partial);
+    IPR_LAUNCH_CHECK();
+    bn_bwd_finalize_kernel<<<(channels + 255) / 256, 256, 0, st>>>(partial, (int)ctas, channels, (double)rows, gamma, mean,
+                                                                  rstd, dgamma, dbeta, accumulate, sign, gamma0,
+                                                                  sign_scale, coef);
+    IPR_LAUNCH_CHECK();
+    const long long n_vec = (long long)rows * c_vec;
+    bn_bwd_apply_kernel<<<grid_1d(n_vec, 256), 256, 0, st>>>((const uint4 *)dy, (const uint4 *)xraw, (const uint4 *)act,
+                                                             coef, (uint4 *)dx, n_vec, c_vec);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" int ipr_dfc_fwd_bf16(const void *a, const float *w, const float *sigma, const float *bias,
+                                float *logits, int batch, int k, ipr_stream_t stream)
+{
+    IPR_REQUIRE(a && w && logits, IPR_E_NULL);
+    IPR_REQUIRE(batch > 0 && k > 0 && k % 8 == 0, IPR_E_SHAPE);
+    IPR_REQUIRE(ipr_aligned16(a) && ipr_aligned16(w), IPR_E_ALIGN);
+    dfc_fwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, ipr_cu(stream)>>>((const uint4 *)a, w, sigma, bias, logits, batch, k / 8);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigma, const float *dlogit,
+                                void *da, float *dw, int accumulate_dw, float slope, int batch, int k,
+                                ipr_stream_t stream)
+{
+    IPR_REQUIRE(a && w && dlogit && da, IPR_E_NULL);
+    IPR_REQUIRE(batch > 0 && k > 0 && k % 8 == 0, IPR_E_SHAPE);
+    IPR_REQUIRE(ipr_aligned16(a) && ipr_aligned16(w) && ipr_aligned16(da), IPR_E_ALIGN);
+    const long long n_vec = (long long)batch * k / 8;
+    dfc_bwd_data_kernel<<<grid_1d(n_vec, 256), 256, 0, ipr_cu(stream)>>>((const uint4 *)a, w, sigma, dlogit, (uint4 *)da,
+                                                                        n_vec, k / 8, slope);
+    IPR_LAUNCH_CHECK();
+    if (dw) {
+        dfc_bwd_weight_kernel<<<(k + 255) / 256, 256, 0, ipr_cu(stream)>>>((const __nv_bfloat16 *)a, dlogit, dw, batch, k,
+                                                                         accumulate_dw);
+        IPR_LAUNCH_CHECK();
+    }
+    return IPR_OK;
+}

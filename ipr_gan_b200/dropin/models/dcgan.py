@@ -46,7 +46,13 @@ class DCGAN(Model):
 
     def forward_g(self, data):
         self.generated = data["fake_sample"]
-        self.gen_logits = self.D(self.generated)
+        # the generator step needs dD/dx only; the reference also fills D's .grad here but zeroes it before
+        # its next use (models/dcgan.py:67), so the weight-gradient GEMMs are skipped
+        self.D.module._ipr_skip_param_grads = True
+        try:
+            self.gen_logits = self.D(self.generated)
+        finally:
+            self.D.module._ipr_skip_param_grads = False
 
     def get_metrics(self):
         vals = torch.stack([self.LossD, self.LossR, self.LossF, self.LossG, self.LossA]).tolist()  # one D2H copy

@@ -16,7 +16,7 @@ from torch.nn.utils import spectral_norm as _sn
 
 
 def _backend():
-    return os.environ.get("IPR_NET_BACKEND", "torch")
+    return os.environ.get("IPR_NET_BACKEND", "native")
 
 
 class ConvGenerator(nn.Module):

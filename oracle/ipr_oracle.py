@@ -411,3 +411,90 @@ def synth_step_inputs(batch, seed=1234):
     real = torch.randn(batch, 3, 32, 32, generator=g).clamp(-1, 1)
     z = torch.randn(batch, 128, generator=g)
     return real, z
+
+
+# --------------------------------------------------------------------------------------------
+# bf16-matched variants of the two networks: SAME fp32 PyTorch operators as above, with values
+# rounded to bf16 at exactly the points where the sm_100a engine stores bf16 (packed weights,
+# inter-layer activations, inter-layer gradients).  The engine's tensor-core path accumulates in
+# fp32, so against THIS model it should agree to accumulation-order noise; against the pure fp32
+# model the difference is dominated by ReLU-mask flips caused by the bf16 activation rounding
+# (measured in DESIGN.md), which no kernel can remove.
+# --------------------------------------------------------------------------------------------
+class _RoundBoth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+class _RoundFwd(torch.autograd.Function):          # weights: rounded copy, straight-through gradient
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+def gen_forward_sim_bf16(G, z):
+    """make_generator() module evaluated with the engine's bf16 rounding points (training-mode BatchNorm)."""
+    r, wq = _RoundBoth.apply, _RoundFwd.apply
+    fc = G.fc[0]
+    h = r(F.relu(F.linear(_RoundFwd.apply(z), wq(fc.weight), fc.bias)))
+    x = h.view(z.size(0), -1, G.mg, G.mg)
+    for i in range(3):
+        conv, bn = G.convs[i][0], G.convs[i][1]
+        raw = r(F.conv_transpose2d(x, wq(conv.weight), stride=2, padding=1))
+        use_batch = bn.training or not bn.track_running_stats
+        upd = bn.training and bn.track_running_stats
+        y = F.batch_norm(raw, bn.running_mean if (upd or not use_batch) else None,
+                         bn.running_var if (upd or not use_batch) else None, bn.weight, bn.bias,
+                         use_batch, bn.momentum, bn.eps)
+        x = r(F.relu(y))
+    pre = _RoundBwd.apply(F.conv_transpose2d(x, wq(G.convs[3].weight), stride=1, padding=1))
+    return torch.tanh(pre)
+
+
+def dis_forward_sim_bf16(D, x):
+    """make_discriminator() module evaluated with the engine's bf16 rounding points; performs the same
+    in-place power iteration on weight_u / weight_v as torch.nn.utils.spectral_norm does in training mode."""
+    r, wq = _RoundBoth.apply, _RoundFwd.apply
+    net = D.net
+    convs = [net[0][0], net[0][2], net[1][0], net[1][2], net[2][0], net[2][2], net[3]]
+    strides = [1, 2, 1, 2, 1, 2, 1]
+
+    def sigma_of(layer):
+        w = layer.weight_orig
+        mat = w.reshape(w.shape[0], -1)
+        u, v = layer.weight_u, layer.weight_v
+        if D.training:
+            with torch.no_grad():
+                nv = torch.mv(mat.t(), u)
+                v.copy_(nv / nv.norm().clamp_min(1e-12))
+                nu = torch.mv(mat, v)
+                u.copy_(nu / nu.norm().clamp_min(1e-12))
+        return torch.dot(u.clone(), torch.mv(mat, v.clone()))
+
+    a = _RoundFwd.apply(x)
+    for layer, s in zip(convs, strides):
+        sig = sigma_of(layer)
+        y = F.conv2d(a, wq(layer.weight_orig), None, stride=s, padding=1) / sig + layer.bias.view(1, -1, 1, 1)
+        a = r(F.leaky_relu(y, 0.1))
+    fc = net[6]
+    sig = sigma_of(fc)
+    return (F.linear(a.flatten(1), fc.weight_orig) / sig + fc.bias).view(-1)
