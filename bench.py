@@ -1,0 +1,294 @@
+"""bench.py -- IPR-DCGAN 32x32 protected training steps/sec on N B200s (BASELINE.json metric, configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W                      # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W      # the reference's CPU path (oracle port)
+
+A "step" is one full protected training step (experiments/image_generation.py:86-101): update_d + update_g
+with the black-box trigger / SSIM watermark loss and the white-box sign loss, global batch 512 split evenly over
+the ranks (strong scaling), synthetic CIFAR-shaped data, random-init weights.  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "IPR-DCGAN 32x32 protected train steps/sec (global batch 512)"
+GLOBAL_BATCH = 512
+FLOP_PER_SAMPLE = 2.970e9          # necessary work of one protected step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="global batch (default: the metric's 512)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_steps_per_sec(steps, warmup, sample_batch=64):
+    """The reference's CPU implementation of the step (oracle port of models/dcgan.py + models/wrappers.py,
+    pinned to the unmodified reference by tests/golden/dcgan_step.npz), all host threads, on a bounded sample:
+    batch 64 (BASELINE configs[0]) per step, converted to steps/s at the metric's global batch."""
+    import torch
+    from oracle import ipr_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1234)
+    G, D = orc.make_generator(), orc.make_discriminator()
+    mark = os.path.join(ROOT, "ipr_gan_b200", "assets", "watermark_a.png")
+    fg, bg = orc.load_watermark(mark, 16, True, True)
+    ref = orc.DCGANStepOracle(G, D, orc.transform_dist, lambda y: orc.paste_patch(y, fg, bg, "tl", 16))
+    real, z = orc.synth_step_inputs(sample_batch)
+    for _ in range(warmup):
+        ref.step(real, z)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.step(real, z)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 60)), max(1, min(args.warmup, 3))
+    sample = 64
+    sps, dt, cores = cpu_reference_steps_per_sec(steps, warmup, sample)
+    value = sps * sample / args.batch
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "IPR-DCGAN 32x32 protected step, global batch %d" % args.batch,
+                   "note": "reference CPU path (PyTorch CPU, oracle port pinned to the reference)"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps at batch %d (configs[0]) in %.1f s; steps/s scaled by %d/%d"
+                                   % (steps, sample, dt, sample, args.batch)},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA (no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert args.batch % world == 0
+    local_batch = args.batch // world
+
+    from ipr_gan_b200 import _lib, dense
+    from ipr_gan_b200.trainer import ProtectedDCGANTrainer
+    tr = ProtectedDCGANTrainer(local_batch, device, use_graph=not args.no_graph)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    real_h = torch.randn(local_batch, 3, 32, 32, generator=gen).clamp(-1, 1).pin_memory()
+    z_h = torch.randn(local_batch, 128, generator=gen).pin_memory()
+    tr.set_inputs(real_h, z_h)
+    tr.capture()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=device)       # 256 MiB > 126 MB of L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """sum of per-step device times (CUDA events around each step, L2 flushed in between), max over ranks"""
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        total = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([total], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(3, args.warmup)):
+        tr.step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(tr.step, args.steps)
+    # end to end through the public call: pinned host batch in, metrics dict out, every step
+    metrics_box = {}
+
+    def e2e_step():
+        metrics_box["m"] = tr.step_from_host(real_h, z_h)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_ms = timed(e2e_step, args.steps)
+    wall_e2e = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # live tensor-roofline measurement: one eager step with CUDA events around every GEMM launch
+    dense.PROFILE = []
+    tr._step()
+    torch.cuda.synchronize()
+    gemm_ms = sum(a.elapsed_time(b) for _, _, a, b in dense.PROFILE)
+    gemm_flops = sum(f for _, f, _, _ in dense.PROFILE)
+    n_gemm = len(dense.PROFILE)
+    by_kind = {}
+    for kind, f, a, b in dense.PROFILE:
+        e = by_kind.setdefault(kind, [0.0, 0.0, 0])
+        e[0] += f
+        e[1] += a.elapsed_time(b)
+        e[2] += 1
+    dense.PROFILE = None
+
+    # HBM-roofline figure of the SSIM loss kernel at this rank's training shape and at a large batch
+    from ipr_gan_b200 import ops
+    pk, pk_src = peaks()
+
+    def ssim_gbs(B):
+        x = torch.rand(B, 3, 32, 32, device=device)
+        y = torch.rand(B, 3, 32, 32, device=device)
+        for _ in range(3):
+            ops.ssim_loss_fwd_bwd(x, y, True)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.ssim_loss_fwd_bwd(x, y, True)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return 36.0 * B * 32 * 32 / (ts[len(ts) // 2] * 1e-3) / 1e9
+    ssim_small, ssim_big = ssim_gbs(local_batch), ssim_gbs(16384)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms = total_ms / args.steps
+    value = 1e3 / ms
+    e2e_value = 1e3 / (e2e_ms / args.steps)
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    peak_tf = pk.get("bf16_tflops_sustained", 1400.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "IPR-DCGAN 32x32 (ConvGenerator32 + SNDiscriminator32) protected step: TransformDist "
+                               "trigger, 16x16 opaque watermark, SSIM loss lambda=1, sign loss gamma0=0.1 'EXAMPLE A'",
+                   "global_batch": args.batch, "per_gpu_batch": local_batch, "parallelism": "dp%d" % world,
+                   "cuda_graph": not args.no_graph, "l2": "flushed (256 MiB memset) between timed steps",
+                   "timing": "sum of per-step CUDA-event times, max over ranks"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "steps/s",
+                "h2d_bytes_per_step": int(real_h.numel() * 4 + z_h.numel() * 4) * world,
+                "d2h_bytes_per_step": 7 * 4 * world, "wall_s": wall_e2e,
+                "call": "ProtectedDCGANTrainer.step_from_host(real_cpu, latent_cpu) -> metrics dict"},
+        "gpu_launches": int(tr.launches_per_step or 0) * args.steps,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf, "traffic": None,
+                     "kernel": "tapgemm_kernel + wgrad_kernel (tcgen05 implicit GEMM), %d launches/step" % n_gemm,
+                     "peak_source": pk_src + " bf16_tflops_sustained",
+                     "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms,
+                     "step_model_flops_tflops": FLOP_PER_SAMPLE * args.batch / world / (ms * 1e-3) / 1e12,
+                     "by_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, "ms": v[1], "launches": v[2]}
+                                 for k, v in sorted(by_kind.items())}},
+        "roofline_ssim": {"bound": "hbm", "unit": "GB/s", "peak": pk.get("hbm_gbs"), "peak_source": pk_src,
+                          "achieved_at_step_batch": ssim_small, "achieved_at_16384": ssim_big,
+                          "frac_at_16384": ssim_big / pk.get("hbm_gbs", 6650.0),
+                          "note": "36*B*H*W algorithmic bytes; the kernel is fp32-FMA-issue bound, see DESIGN.md"},
+        "last_metrics": metrics_box.get("m"),
+    }
+    if not args.skip_cpu_baseline and world == 1:
+        sps, dt, cores = cpu_reference_steps_per_sec(6, 1, 64)
+        line["cpu_baseline"] = {"value": sps * 64 / args.batch, "unit": "steps/s", "cores": cores, "kind": "port",
+                                "sample": "6 steps at batch 64 (configs[0]) in %.1f s; steps/s scaled by 64/%d"
+                                          % (dt, args.batch)}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -14,6 +14,26 @@ from . import _lib
 from ._lib import check, lib
 
 MAX_TAPS, MAX_PHASES = 16, 4
+
+# When set to a list, every GEMM launch appends (kind, algorithmic_flops, start_event, end_event): bench.py uses
+# it for the live tensor-roofline measurement (CUDA events on the launching stream).
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(kind, flops, start):
+    if start is None:
+        return
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    PROFILE.append((kind, flops, start, ev))
 EPI_LINEAR, EPI_BIAS_LRELU, EPI_MASK, EPI_TANH_NCHW, EPI_LINEAR_F32, EPI_LINEAR_NCHW = 0, 1, 2, 3, 4, 5
 
 
@@ -164,9 +184,15 @@ class Plan(object):
                 check(tiles, "ipr_tapgemm_m_tiles")
             stats = torch.empty(tiles * self.n_phases * 4, 2, self.n_total, device=a.device, dtype=torch.float32)
             d.stats = stats.data_ptr()
+        ev = _prof_begin()
         check(L.ipr_tapgemm_bf16(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
               "ipr_tapgemm_bf16(%s)" % self.kind)
+        _prof_end("tapgemm:" + self.kind, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps * self.k_valid() * nv, ev)
         return out, stats
+
+    def k_valid(self):
+        """Channels per tap that carry data (the 3-channel patch layers pad 27 -> 64)."""
+        return getattr(self, "k_valid_override", self.cin)
 
 
 class WGrad(ctypes.Structure):
@@ -261,7 +287,10 @@ class WGradPlan(object):
         ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
         d.workspace = ws.data_ptr()
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ev = _prof_begin()
         check(L.ipr_wgrad_bf16(ctypes.byref(d), st), "ipr_wgrad_bf16(%s)" % self.fwd.kind)
+        _prof_end("wgrad:" + self.fwd.kind, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps *
+                  getattr(self, "k_valid_override", xc) * getattr(self, "rows_valid_override", self.rows), ev)
         col_off, row_map = self._tables(x.device)
         check(L.ipr_wgrad_reduce_f32(ws.data_ptr(), splits, self.n_phases, self.rows, self.k_total,
                                      col_off.data_ptr(), row_map.data_ptr() if row_map is not None else None,

@@ -154,6 +154,8 @@ class GenPlans(object):
         self.last_dg = dense.Plan("linear", 64, 64)                    # d(a3) = patches(dY) x W'
         self.last_wg = dense.WGradPlan(dense.Plan("linear", 64, 64), (64, 3, 3, 3), col_off=_col_off_patch27(True),
                                        s_n=27)
+        self.last_dg.k_valid_override = 27            # flop accounting: 27 of the 64 patch columns carry data
+        self.last_wg.k_valid_override = 27
         self.packs = _Packs()
         self._perm_dev = {}
         _ALL_PACKS.append(self.packs)
@@ -188,6 +190,8 @@ class DisPlans(object):
         hw = torch.arange(md * md).view(-1, 1)
         c = torch.arange(512).view(1, -1)
         self.perm = (c * (md * md) + hw).reshape(-1)                    # NHWC feature n' -> reference feature
+        self.first.k_valid_override = 27
+        self.first_wg.k_valid_override = 27
         self.packs = _Packs()
         self._perm_dev = {}
         _ALL_PACKS.append(self.packs)
