@@ -276,6 +276,45 @@ int ipr_dfc_fwd_bf16(const void *a, const float *w, const float *sigma, const fl
 int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigma, const float *dlogit, void *da, float *dw,
                      int accumulate_dw, float slope, int batch, int k, ipr_stream_t stream);
 
+/* Column sums: out[c] (+)= scale * sum_r in[r][c].  `_partials_f32` reduces fp32 partial rows (the GEMM epilogue's
+ * per-warp column statistics); `_bf16` reduces an NHWC bf16 tensor over its pixels (bias gradients).
+ * Two launches each, fixed summation order (deterministic).  Workspace: ipr_colsum_workspace_bytes(ncols). */
+size_t ipr_colsum_workspace_bytes(int ncols);
+int ipr_colsum_partials_f32(const float *partial, int rows, int ncols, float *out, int accumulate, float scale,
+                            void *workspace, size_t workspace_bytes, ipr_stream_t stream);
+int ipr_colsum_bf16(const void *x, int64_t rows, int channels, float *out, int accumulate, float scale,
+                    void *workspace, size_t workspace_bytes, ipr_stream_t stream);
+
+/* ------------------------------------------------------------------ spectral norm, optimizer, weight packing */
+
+#define IPR_SN_MAX_LAYERS 16
+typedef struct {
+    const float *w;        /* fp32 master weight viewed as (rows, cols) row-major (weight_orig)            */
+    float *u, *v;          /* power-iteration vectors (weight_u: rows, weight_v: cols), updated in place     */
+    float *sigma;          /* device scalar written by the power iteration, read by the weight gradient     */
+    float *grad;           /* ipr_sn_weight_grad_f32: gradient w.r.t. W/sigma in, w.r.t. W out (in place)   */
+    int32_t rows, cols;
+    int64_t scratch_off;   /* offset (floats) of this layer's private slice of `scratch`,
+                              at least ipr_sn_scratch_floats(rows, cols) long                               */
+} ipr_sn_layer_t;
+
+size_t ipr_sn_scratch_floats(int rows, int cols);
+/* One power iteration for every layer (update != 0; training forward) or just sigma = u.(W v) (update == 0; eval),
+ * exactly as torch.nn.utils.spectral_norm does per layer and per forward (networks/sn_discriminator.py:1). */
+int ipr_sn_power_iter_f32(const ipr_sn_layer_t *layers_host, int n_layers, int update, float eps, float *scratch,
+                          ipr_stream_t stream);
+/* grad <- (grad - <grad, W>/sigma * u v^T) / sigma for every layer: backward of W -> W / sigma(W). */
+int ipr_sn_weight_grad_f32(const ipr_sn_layer_t *layers_host, int n_layers, float *scratch, ipr_stream_t stream);
+
+/* Adam (torch.optim.Adam semantics, models/dcgan.py:21-24) over flat fp32 arenas in one launch; *step (device
+ * float) is read then incremented on the device, so the call is CUDA-graph replayable. */
+int ipr_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, float *step, ipr_stream_t stream);
+
+/* dst[i] = bf16(index[i] >= 0 ? src[index[i]] : 0), n % 8 == 0: rebuilds every GEMM operand layout of a network
+ * from its fp32 parameter arena in one launch. */
+int ipr_gather_pack_bf16(const float *src, const int32_t *index, void *dst, int64_t n, ipr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -401,3 +401,86 @@ extern "C" int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigm
     }
     return IPR_OK;
 }
+
+// ------------------------------------------------------------------------------------ column reductions
+namespace {
+
+// stage 1: out[g][c] = sum_{r = g, g+G, ...} in[r][c]      (fp32 partial rows, e.g. GEMM-epilogue statistics)
+__global__ void __launch_bounds__(256)
+colsum_partials_stage1(const float *__restrict__ in, int rows, int ncols, float *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    float acc = 0.0f;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) acc += in[(size_t)r * ncols + c];
+    out[(size_t)blockIdx.y * ncols + c] = acc;
+}
+// stage 2: out[c] (+)= scale * sum_g in[g][c], double accumulation, fixed order
+__global__ void __launch_bounds__(256)
+colsum_stage2(const float *__restrict__ in, int rows, int ncols, float *__restrict__ out, int accumulate, float scale)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double acc = 0.0;
+    for (int r = 0; r < rows; r++) acc += (double)in[(size_t)r * ncols + c];
+    const float v = (float)acc * scale;
+    out[c] = accumulate ? out[c] + v : v;
+}
+// stage 1 for a bf16 [rows][C] tensor: each CTA owns a slab of rows; 8 channels per thread
+__global__ void __launch_bounds__(256)
+colsum_bf16_stage1(const uint4 *__restrict__ x, long long rows, int c_vec, float *__restrict__ out)
+{
+    // grid.x = column groups of 256 vectors, grid.y = row slabs
+    const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cv >= c_vec) return;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.0f;
+    for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+        float f[8];
+        unpack8(__ldg(x + r * c_vec + cv), f);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] += f[k];
+    }
+    float *dst = out + ((size_t)blockIdx.y * c_vec + cv) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) dst[k] = acc[k];
+}
+
+}  // namespace
+
+extern "C" size_t ipr_colsum_workspace_bytes(int ncols) { return (size_t)64 * ncols * sizeof(float); }
+
+extern "C" int ipr_colsum_partials_f32(const float *partial, int rows, int ncols, float *out, int accumulate,
+                                       float scale, void *workspace, size_t workspace_bytes, ipr_stream_t stream)
+{
+    IPR_REQUIRE(partial && out && workspace, IPR_E_NULL);
+    IPR_REQUIRE(rows > 0 && ncols > 0, IPR_E_SHAPE);
+    IPR_REQUIRE(workspace_bytes >= ipr_colsum_workspace_bytes(ncols), IPR_E_WORKSPACE);
+    const int G = rows < 64 ? rows : 64;
+    dim3 grid((ncols + 255) / 256, G);
+    colsum_partials_stage1<<<grid, 256, 0, ipr_cu(stream)>>>(partial, rows, ncols, (float *)workspace);
+    IPR_LAUNCH_CHECK();
+    colsum_stage2<<<(ncols + 255) / 256, 256, 0, ipr_cu(stream)>>>((const float *)workspace, G, ncols, out, accumulate, scale);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" int ipr_colsum_bf16(const void *x, int64_t rows, int channels, float *out, int accumulate, float scale,
+                               void *workspace, size_t workspace_bytes, ipr_stream_t stream)
+{
+    IPR_REQUIRE(x && out && workspace, IPR_E_NULL);
+    IPR_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0, IPR_E_SHAPE);
+    IPR_REQUIRE(workspace_bytes >= ipr_colsum_workspace_bytes(channels), IPR_E_WORKSPACE);
+    IPR_REQUIRE(ipr_aligned16(x), IPR_E_ALIGN);
+    const int c_vec = channels / 8;
+    const int G = rows < 64 ? (int)rows : 64;
+    dim3 grid((c_vec + 255) / 256, G);
+    const int threads = c_vec < 256 ? ((c_vec + 31) / 32) * 32 : 256;
+    colsum_bf16_stage1<<<grid, threads, 0, ipr_cu(stream)>>>((const uint4 *)x, rows, c_vec, (float *)workspace);
+    IPR_LAUNCH_CHECK();
+    colsum_stage2<<<(channels + 255) / 256, 256, 0, ipr_cu(stream)>>>((const float *)workspace, G, channels, out,
+                                                                    accumulate, scale);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}

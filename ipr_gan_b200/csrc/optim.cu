@@ -1,0 +1,103 @@
+// optim.cu -- flat-arena optimizer and weight re-packing.
+//   * ipr_adam_flat_f32: one launch updates EVERY parameter of a network (params / grads / moments live in four
+//     contiguous fp32 arenas), replacing torch.optim.Adam's per-tensor foreach kernels (models/dcgan.py:21-24).
+//     The step counter lives on the device so the launch is CUDA-graph replayable.
+//   * ipr_gather_pack_bf16: one launch rebuilds all bf16 GEMM operand layouts of a network from the fp32 master
+//     arena through a precomputed index table (dst[i] = src[idx[i]], idx < 0 -> 0).
+#include "ipr_common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                 long long n, float lr, float b1, float b2, float eps, float wd, const float *__restrict__ step)
+{
+    const float t = *step + 1.0f;
+    const float bc1 = 1.0f - powf(b1, t);
+    const float bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+    const float step_size = lr / bc1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4 *>(p)[i];
+        const float4 gg = reinterpret_cast<const float4 *>(g)[i];
+        float4 mm = reinterpret_cast<float4 *>(m)[i], vv = reinterpret_cast<float4 *>(v)[i];
+        float *pa = &pp.x; const float *ga = &gg.x; float *ma = &mm.x; float *va = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float gk = ga[k] + wd * pa[k];
+            ma[k] = b1 * ma[k] + (1.0f - b1) * gk;
+            va[k] = b2 * va[k] + (1.0f - b2) * gk * gk;
+            pa[k] -= step_size * ma[k] / (sqrtf(va[k]) / bc2_sqrt + eps);
+        }
+        reinterpret_cast<float4 *>(p)[i] = pp;
+        reinterpret_cast<float4 *>(m)[i] = mm;
+        reinterpret_cast<float4 *>(v)[i] = vv;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gk = g[i] + wd * p[i];
+        m[i] = b1 * m[i] + (1.0f - b1) * gk;
+        v[i] = b2 * v[i] + (1.0f - b2) * gk * gk;
+        p[i] -= step_size * m[i] / (sqrtf(v[i]) / bc2_sqrt + eps);
+    }
+}
+
+__global__ void step_increment_kernel(float *step) { *step += 1.0f; }
+
+__global__ void __launch_bounds__(256)
+gather_pack_kernel(const float *__restrict__ src, const int *__restrict__ idx, __nv_bfloat16 *__restrict__ dst, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n8 = n >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const int4 i0 = __ldg(reinterpret_cast<const int4 *>(idx) + 2 * i);
+        const int4 i1 = __ldg(reinterpret_cast<const int4 *>(idx) + 2 * i + 1);
+        const int id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) f[k] = id[k] >= 0 ? __ldg(src + id[k]) : 0.0f;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+            w[k] = *reinterpret_cast<uint32_t *>(&t);
+        }
+        reinterpret_cast<uint4 *>(dst)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+}  // namespace
+
+extern "C" int ipr_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                                 float lr, float beta1, float beta2, float eps, float weight_decay, float *step,
+                                 ipr_stream_t stream)
+{
+    IPR_REQUIRE(param && grad && exp_avg && exp_avg_sq && step, IPR_E_NULL);
+    IPR_REQUIRE(n > 0, IPR_E_SHAPE);
+    IPR_REQUIRE(ipr_aligned16(param) && ipr_aligned16(grad) && ipr_aligned16(exp_avg) && ipr_aligned16(exp_avg_sq),
+                IPR_E_ALIGN);
+    long long blocks = (n / 4 + 255) / 256;
+    const long long cap = (long long)ipr_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    adam_flat_kernel<<<(unsigned)blocks, 256, 0, ipr_cu(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                  eps, weight_decay, step);
+    IPR_LAUNCH_CHECK();
+    step_increment_kernel<<<1, 1, 0, ipr_cu(stream)>>>(step);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" int ipr_gather_pack_bf16(const float *src, const int32_t *index, void *dst, int64_t n, ipr_stream_t stream)
+{
+    IPR_REQUIRE(src && index && dst, IPR_E_NULL);
+    IPR_REQUIRE(n > 0 && n % 8 == 0, IPR_E_SHAPE);
+    IPR_REQUIRE(ipr_aligned16(index) && ipr_aligned16(dst), IPR_E_ALIGN);
+    long long blocks = (n / 8 + 255) / 256;
+    const long long cap = (long long)ipr_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    gather_pack_kernel<<<(unsigned)blocks, 256, 0, ipr_cu(stream)>>>(src, index, (__nv_bfloat16 *)dst, n);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}

@@ -1,0 +1,204 @@
+// sn.cu -- spectral normalisation of the discriminator (torch.nn.utils.spectral_norm semantics,
+// networks/sn_discriminator.py:1,9-21), batched over ALL layers of the network:
+//   power iteration   v <- normalize(W^T u);  u <- normalize(W v);  sigma = u . (W v)      (4 launches, any #layers)
+//   weight gradient   dW = (G - <G, W>/sigma * u v^T) / sigma                               (2 launches)
+// The reference runs ~15 tiny PyTorch/cuBLAS kernels per layer and per forward for the former and an autograd
+// chain for the latter.  W is the fp32 master weight viewed as (rows = out channels, cols = rest).
+#include "ipr_common.cuh"
+
+namespace {
+
+struct SnTable {
+    ipr_sn_layer_t layer[IPR_SN_MAX_LAYERS];
+    int n_layers;
+    int cta_begin[IPR_SN_MAX_LAYERS + 1];      // prefix sums of CTAs per layer for the current kernel
+};
+
+__device__ __forceinline__ int find_layer(const SnTable &t, int cta) {
+    int l = 0;
+    while (l + 1 < t.n_layers && cta >= t.cta_begin[l + 1]) l++;
+    return l;
+}
+
+constexpr int ROW_CHUNK = 32;
+
+// A1: partial_t[layer][row_chunk][col] = sum_{rows in chunk} W[row][col] * u[row]
+__global__ void __launch_bounds__(256)
+sn_wtu_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
+{
+    const int l = find_layer(tab, blockIdx.x);
+    const ipr_sn_layer_t L = tab.layer[l];
+    const int local = blockIdx.x - tab.cta_begin[l];
+    const int col_ctas = (L.cols + 255) / 256;
+    const int rc = local / col_ctas, cc = local - rc * col_ctas;
+    const int col = cc * 256 + threadIdx.x;
+    if (col >= L.cols) return;
+    const int r0 = rc * ROW_CHUNK, r1 = min(L.rows, r0 + ROW_CHUNK);
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int r = r0; r < r1; r++) acc += L.w[(size_t)r * L.cols + col] * L.u[r];
+    scratch[L.scratch_off + (size_t)rc * L.cols + col] = acc;
+}
+
+// A2 (one CTA per layer): t = sum of partials; v = t / max(||t||, eps)
+__global__ void __launch_bounds__(1024)
+sn_v_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scratch, float eps)
+{
+    __shared__ float red[32];
+    const ipr_sn_layer_t L = tab.layer[blockIdx.x];
+    const int chunks = (L.rows + ROW_CHUNK - 1) / ROW_CHUNK;
+    float ss = 0.0f;
+    for (int c = threadIdx.x; c < L.cols; c += blockDim.x) {
+        float t = 0.0f;
+        for (int k = 0; k < chunks; k++) t += scratch[L.scratch_off + (size_t)k * L.cols + c];
+        L.v[c] = t;
+        ss += t * t;
+    }
+    const float tot = ipr_block_sum(ss, red);
+    const float inv = 1.0f / fmaxf(sqrtf(tot), eps);
+    for (int c = threadIdx.x; c < L.cols; c += blockDim.x) L.v[c] *= inv;
+}
+
+// B1: s[row] = W[row,:] . v     (one warp per row)
+__global__ void __launch_bounds__(256)
+sn_wv_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
+{
+    const int l = find_layer(tab, blockIdx.x);
+    const ipr_sn_layer_t L = tab.layer[l];
+    const int row = (blockIdx.x - tab.cta_begin[l]) * 8 + (threadIdx.x >> 5);
+    if (row >= L.rows) return;
+    const int lane = threadIdx.x & 31;
+    const float *w = L.w + (size_t)row * L.cols;
+    float acc = 0.0f;
+    for (int c = lane; c < L.cols; c += 32) acc += w[c] * L.v[c];
+    acc = ipr_warp_sum(acc);
+    if (lane == 0) scratch[L.scratch_off + row] = acc;
+}
+
+// B2 (one CTA per layer): update: u = s / max(||s||, eps), sigma = u . s ; no update: sigma = u_old . s
+__global__ void __launch_bounds__(1024)
+sn_u_sigma_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scratch, float eps, int update)
+{
+    __shared__ float red[32];
+    const ipr_sn_layer_t L = tab.layer[blockIdx.x];
+    float acc = 0.0f;
+    for (int r = threadIdx.x; r < L.rows; r += blockDim.x) {
+        const float s = scratch[L.scratch_off + r];
+        acc += update ? s * s : s * L.u[r];
+    }
+    const float tot = ipr_block_sum(acc, red);
+    if (update) {
+        const float inv = 1.0f / fmaxf(sqrtf(tot), eps);
+        for (int r = threadIdx.x; r < L.rows; r += blockDim.x) L.u[r] = scratch[L.scratch_off + r] * inv;
+        if (threadIdx.x == 0) *L.sigma = tot * inv;          // u . s = ||s||^2 / max(||s||, eps)
+    } else if (threadIdx.x == 0) {
+        *L.sigma = tot;
+    }
+}
+
+// C1: per-CTA partial of <G, W>;  C2: G <- (G - (<G,W>/sigma) u v^T) / sigma   (in place)
+constexpr int DOT_CTAS = 32;
+
+__global__ void __launch_bounds__(256)
+sn_dot_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
+{
+    __shared__ float red[32];
+    const int l = blockIdx.x / DOT_CTAS, part = blockIdx.x - l * DOT_CTAS;
+    const ipr_sn_layer_t L = tab.layer[l];
+    const long long n = (long long)L.rows * L.cols;
+    float acc = 0.0f;
+    for (long long i = (long long)part * 256 + threadIdx.x; i < n; i += (long long)DOT_CTAS * 256) acc += L.grad[i] * L.w[i];
+    const float tot = ipr_block_sum(acc, red);
+    if (threadIdx.x == 0) scratch[L.scratch_off + part] = tot;
+}
+
+__global__ void __launch_bounds__(256)
+sn_grad_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scratch)
+{
+    const int l = find_layer(tab, blockIdx.x);
+    const ipr_sn_layer_t L = tab.layer[l];
+    float dot = 0.0f;
+    for (int k = 0; k < DOT_CTAS; k++) dot += scratch[L.scratch_off + k];
+    const float sigma = *L.sigma;
+    const float coef = dot / sigma;
+    const float inv = 1.0f / sigma;
+    const long long n = (long long)L.rows * L.cols;
+    const long long i = (long long)(blockIdx.x - tab.cta_begin[l]) * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int r = (int)(i / L.cols), c = (int)(i - (long long)r * L.cols);
+    L.grad[i] = (L.grad[i] - coef * L.u[r] * L.v[c]) * inv;
+}
+
+int fill(SnTable &t, const ipr_sn_layer_t *layers, int n)
+{
+    IPR_REQUIRE(layers, IPR_E_NULL);
+    IPR_REQUIRE(n > 0 && n <= IPR_SN_MAX_LAYERS, IPR_E_SHAPE);
+    for (int i = 0; i < n; i++) {
+        IPR_REQUIRE(layers[i].w && layers[i].u && layers[i].v && layers[i].sigma, IPR_E_NULL);
+        IPR_REQUIRE(layers[i].rows > 0 && layers[i].cols > 0, IPR_E_SHAPE);
+        t.layer[i] = layers[i];
+    }
+    t.n_layers = n;
+    return IPR_OK;
+}
+
+}  // namespace
+
+extern "C" size_t ipr_sn_scratch_floats(int rows, int cols)
+{
+    const size_t a = (size_t)((rows + ROW_CHUNK - 1) / ROW_CHUNK) * cols;
+    const size_t b = (size_t)rows > (size_t)DOT_CTAS ? (size_t)rows : (size_t)DOT_CTAS;
+    return (a > b ? a : b) + 32;
+}
+
+extern "C" int ipr_sn_power_iter_f32(const ipr_sn_layer_t *layers_host, int n_layers, int update, float eps,
+                                     float *scratch, ipr_stream_t stream)
+{
+    SnTable t;
+    int rc = fill(t, layers_host, n_layers);
+    if (rc != IPR_OK) return rc;
+    IPR_REQUIRE(scratch, IPR_E_NULL);
+    cudaStream_t st = ipr_cu(stream);
+    if (update) {
+        int total = 0;
+        for (int i = 0; i < n_layers; i++) {
+            t.cta_begin[i] = total;
+            total += ((t.layer[i].rows + ROW_CHUNK - 1) / ROW_CHUNK) * ((t.layer[i].cols + 255) / 256);
+        }
+        t.cta_begin[n_layers] = total;
+        sn_wtu_kernel<<<total, 256, 0, st>>>(t, scratch);
+        IPR_LAUNCH_CHECK();
+        sn_v_kernel<<<n_layers, 1024, 0, st>>>(t, scratch, eps);
+        IPR_LAUNCH_CHECK();
+    }
+    int total = 0;
+    for (int i = 0; i < n_layers; i++) { t.cta_begin[i] = total; total += (t.layer[i].rows + 7) / 8; }
+    t.cta_begin[n_layers] = total;
+    sn_wv_kernel<<<total, 256, 0, st>>>(t, scratch);
+    IPR_LAUNCH_CHECK();
+    sn_u_sigma_kernel<<<n_layers, 1024, 0, st>>>(t, scratch, eps, update);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" int ipr_sn_weight_grad_f32(const ipr_sn_layer_t *layers_host, int n_layers, float *scratch,
+                                      ipr_stream_t stream)
+{
+    SnTable t;
+    int rc = fill(t, layers_host, n_layers);
+    if (rc != IPR_OK) return rc;
+    IPR_REQUIRE(scratch, IPR_E_NULL);
+    for (int i = 0; i < n_layers; i++) IPR_REQUIRE(t.layer[i].grad, IPR_E_NULL);
+    cudaStream_t st = ipr_cu(stream);
+    sn_dot_kernel<<<n_layers * DOT_CTAS, 256, 0, st>>>(t, scratch);
+    IPR_LAUNCH_CHECK();
+    int total = 0;
+    for (int i = 0; i < n_layers; i++) {
+        t.cta_begin[i] = total;
+        total += (int)(((long long)t.layer[i].rows * t.layer[i].cols + 255) / 256);
+    }
+    t.cta_begin[n_layers] = total;
+    sn_grad_kernel<<<total, 256, 0, st>>>(t, scratch);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}

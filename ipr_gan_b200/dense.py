@@ -111,8 +111,9 @@ class Plan(object):
             raise ValueError(kind)
         self.n_taps = len(self.taps[0])
 
-    # weight (fp32, reference layout) -> bf16 [phase][n_total][taps*cin]
-    def pack(self, w, perm=None):
+    # weight (reference layout) -> [phase][n_total][taps*cin] in the SAME dtype (zeros where padded); works on
+    # index tensors too, which is how the gather tables of engine.PackSet are derived
+    def pack_layout(self, w, perm=None):
         k = self.kind
         if k == "linear":
             m = w if perm is None else w[perm]
@@ -131,10 +132,13 @@ class Plan(object):
                     else:                                            # convT4s2_dgrad: n = I, c = O
                         cols.append(w[:, :, kh, kw])
                 mats.append(torch.cat(cols, dim=1))
-        out = torch.zeros(self.n_phases, self.n_total, mats[0].shape[1], device=w.device, dtype=torch.bfloat16)
+        out = torch.zeros(self.n_phases, self.n_total, mats[0].shape[1], device=w.device, dtype=w.dtype)
         for i, m in enumerate(mats):
-            out[i, :m.shape[0]] = m.to(torch.bfloat16)
+            out[i, :m.shape[0]] = m
         return out.contiguous()
+
+    def pack(self, w, perm=None):
+        return self.pack_layout(w, perm).to(torch.bfloat16)
 
     def out_hw(self, a_h, a_w):
         if self.kind in ("conv4s2", "convT4s2_dgrad"):

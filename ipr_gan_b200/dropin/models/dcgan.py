@@ -22,6 +22,10 @@ class DCGAN(Model):
 
         make_opt = getattr(optim, config.opt)
         kwargs = config.opt_param.to_dict()
+        if config.opt == "Adam" and device[0].type == "cuda":
+            # same class hierarchy and state_dict format as torch.optim.Adam; one flat-arena launch per step,
+            # gradient all-reduce over NCCL when torch.distributed is initialised
+            from ipr_gan_b200.optim import FlatAdam as make_opt
         self.optG = make_opt(self.G.parameters(), **kwargs)
         self.optD = make_opt(self.D.parameters(), **kwargs)
         self._modules.update(G=self.G, D=self.D, optG=self.optG, optD=self.optD)

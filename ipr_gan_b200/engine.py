@@ -20,7 +20,8 @@ import ctypes
 import torch
 import torch.nn as nn
 
-from . import dense
+from . import dense, flat
+from ._lib import SnLayer
 from ._lib import check, lib
 
 BN_EPS_DEFAULT = 1e-5
@@ -43,9 +44,35 @@ def im2col3(x, tanh_out=None):
     return out
 
 
+def colsum_partials(partial, out=None, accumulate=False, scale=1.0):
+    """partial: [rows][ncols] fp32 -> out[ncols] (fixed-order two-stage reduction)."""
+    rows, ncols = partial.shape[0], partial.numel() // partial.shape[0]
+    if out is None:
+        out = torch.empty(ncols, device=partial.device, dtype=torch.float32)
+    nbytes = lib().ipr_colsum_workspace_bytes(ncols)
+    ws = torch.empty(nbytes // 4, device=partial.device, dtype=torch.float32)
+    check(lib().ipr_colsum_partials_f32(_p(partial), rows, ncols, _p(out), int(bool(accumulate)), float(scale),
+                                        _p(ws), nbytes, _st()), "ipr_colsum_partials_f32")
+    return out
+
+
+def colsum_bf16(x2d, out=None, accumulate=False, scale=1.0):
+    """x2d: [rows][C] bf16 -> out[C] fp32."""
+    rows, C = x2d.shape
+    if out is None:
+        out = torch.empty(C, device=x2d.device, dtype=torch.float32)
+    nbytes = lib().ipr_colsum_workspace_bytes(C)
+    ws = torch.empty(nbytes // 4, device=x2d.device, dtype=torch.float32)
+    check(lib().ipr_colsum_bf16(_p(x2d), rows, C, _p(out), int(bool(accumulate)), float(scale), _p(ws), nbytes, _st()),
+          "ipr_colsum_bf16")
+    return out
+
+
 def bn_finalize(stats, count, bn, update_running):
     C = bn.num_features
     dev = stats.device
+    if stats.shape[0] > 8:
+        stats = colsum_partials(stats).view(1, 2, C)
     scale = torch.empty(C, device=dev)
     shift = torch.empty(C, device=dev)
     mean = torch.empty(C, device=dev)
@@ -96,31 +123,51 @@ def dfc_bwd(a, w, sigma, dlogit, want_dw, slope):
 
 
 # ----------------------------------------------------------------------------------------- plan caches
-class _Packs(object):
-    """bf16 packed weight matrices, refreshed when the fp32 master changes (``_version``)."""
+class PackSet(object):
+    """Every bf16 GEMM operand layout of one network, rebuilt from the network's fp32 parameter arena by ONE
+    gather launch (csrc/optim.cu) whenever the masters changed."""
 
-    def __init__(self):
-        self.store = {}
+    def __init__(self, module, specs):
+        self.arena = flat.arena_for(list(module.parameters()))
+        dev = self.arena.param.device
+        parts, self.slices, off = [], {}, 0
+        for key, param, layout_fn in specs:
+            o = self.arena.offset_of(param)
+            src = (torch.arange(param.numel(), dtype=torch.float64) + (o + 1)).view(param.shape)   # 0 = padding
+            lay = layout_fn(src)
+            idx = (lay.reshape(-1).to(torch.int64) - 1).to(torch.int32)
+            n = idx.numel()
+            pad = (-n) % 8
+            if pad:
+                idx = torch.cat([idx, torch.full((pad,), -1, dtype=torch.int32)])
+            self.slices[key] = (off, n, tuple(lay.shape))
+            parts.append(idx)
+            off += n + pad
+        self.index = torch.cat(parts).to(dev)
+        self.buf = torch.empty(off, device=dev, dtype=torch.bfloat16)
+        self.stamp = None
 
-    def get(self, key, param, fn):
-        ver = (param._version, param.data_ptr())
-        hit = self.store.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
-        with torch.no_grad():
-            val = fn(param.detach())
-        self.store[key] = (ver, val)
-        return val
+    def refresh(self):
+        stamp = (self.arena.param._version, self.arena.version)
+        if stamp != self.stamp:
+            check(lib().ipr_gather_pack_bf16(_p(self.arena.param), _p(self.index), _p(self.buf), self.buf.numel(), _st()),
+                  "ipr_gather_pack_bf16")
+            self.stamp = stamp
+
+    def get(self, key):
+        self.refresh()
+        off, n, shape = self.slices[key]
+        return self.buf[off:off + n].view(shape)
 
     def clear(self):
-        self.store.clear()
+        self.stamp = None
 
 
 _ALL_PACKS = []
 
 
 def reset_caches():
-    """Drop every cached weight pack (call before CUDA-graph capture so packing is part of the graph)."""
+    """Mark every packed-weight set stale (call before CUDA-graph capture so packing is part of the graph)."""
     for p in _ALL_PACKS:
         p.clear()
 
@@ -133,6 +180,14 @@ def _col_off_patch27(n_is_first):
             for c in range(3):
                 off[0, (kh * 3 + kw) * 3 + c] = c * 9 + kh * 3 + kw
     return off
+
+
+def _patch27_layout(w):
+    """(n, 3, 3, 3)-shaped weight -> [1][64][64]: row n, column k = (kh*3+kw)*3 + c (conv: c = in channel of an
+    (O, 3, kh, kw) weight; convT: c = out channel of an (I, 3, kh, kw) weight)."""
+    m = torch.zeros(1, 64, 64, device=w.device, dtype=w.dtype)
+    m[0, :, :27] = w.permute(0, 2, 3, 1).reshape(64, 27)
+    return m
 
 
 class GenPlans(object):
@@ -156,8 +211,16 @@ class GenPlans(object):
                                        s_n=27)
         self.last_dg.k_valid_override = 27            # flop accounting: 27 of the 64 patch columns carry data
         self.last_wg.k_valid_override = 27
-        self.packs = _Packs()
         self._perm_dev = {}
+        cv = module.convs
+        perm = self.perm
+        specs = [("fc", module.fc[0].weight, lambda w: self.fc.pack_layout(w, perm))]
+        for i in range(3):
+            specs.append(("ct%d" % i, cv[i][0].weight, self.ct[i].pack_layout))
+            specs.append(("ct%d_dg" % i, cv[i][0].weight, self.ct_dg[i].pack_layout))
+        specs.append(("ct3", cv[3].weight, self.last.pack_layout))
+        specs.append(("ct3_dg", cv[3].weight, _patch27_layout))
+        self.packs = PackSet(module, specs)
         _ALL_PACKS.append(self.packs)
 
     def perm_on(self, device):
@@ -165,12 +228,6 @@ class GenPlans(object):
         if key not in self._perm_dev:
             self._perm_dev[key] = self.perm.to(device)
         return self._perm_dev[key]
-
-    def pack_last_dgrad(self, w):
-        # B[n = ci][k = (kh*3+kw)*3 + co] = W[ci, co, kh, kw]
-        m = torch.zeros(1, 64, 64, device=w.device, dtype=torch.bfloat16)
-        m[0, :, :27] = w.permute(0, 2, 3, 1).reshape(64, 27).to(torch.bfloat16)
-        return m
 
 
 class DisPlans(object):
@@ -183,6 +240,8 @@ class DisPlans(object):
         self.first_wg = dense.WGradPlan(dense.Plan("linear", 64, 64), (64, 3, 3, 3), col_off=_col_off_patch27(False),
                                         s_n=27)
         self.first_dg = dense.Plan("conv3_dgrad", 64, 3, n_pad=16)
+        self.first.k_valid_override = 27
+        self.first_wg.k_valid_override = 27
         self.conv = [dense.Plan(k, ci, co) for k, ci, co in specs]
         self.conv_dg = [dense.Plan(k + "_dgrad", co, ci) for k, ci, co in specs]
         self.conv_wg = [dense.WGradPlan(p, (p.cout, p.cin, 3 if p.kind == "conv3" else 4, 3 if p.kind == "conv3" else 4))
@@ -190,11 +249,41 @@ class DisPlans(object):
         hw = torch.arange(md * md).view(-1, 1)
         c = torch.arange(512).view(1, -1)
         self.perm = (c * (md * md) + hw).reshape(-1)                    # NHWC feature n' -> reference feature
-        self.first.k_valid_override = 27
-        self.first_wg.k_valid_override = 27
-        self.packs = _Packs()
         self._perm_dev = {}
+        layers = _sn_layers(module)
+        pk = [("c0", layers[0].weight_orig, _patch27_layout), ("c0_dg", layers[0].weight_orig, self.first_dg.pack_layout)]
+        for i in range(6):
+            pk.append(("c%d" % (i + 1), layers[i + 1].weight_orig, self.conv[i].pack_layout))
+            pk.append(("c%d_dg" % (i + 1), layers[i + 1].weight_orig, self.conv_dg[i].pack_layout))
+        self.packs = PackSet(module, pk)
         _ALL_PACKS.append(self.packs)
+        # power-iteration vectors of all layers in ONE buffer (the module's weight_u / weight_v become views), so a
+        # forward snapshots them with a single copy; per-layer scratch slices for the batched SN kernels
+        dev = layers[0].weight_orig.device
+        sizes = []
+        for l in layers:
+            sizes += [l.weight_u.numel(), l.weight_v.numel()]
+        self.uv = torch.empty(sum(sizes), device=dev, dtype=torch.float32)
+        self.uv_off, off = [], 0
+        with torch.no_grad():
+            for l in layers:
+                nu, nv = l.weight_u.numel(), l.weight_v.numel()
+                self.uv[off:off + nu].copy_(l.weight_u)
+                self.uv[off + nu:off + nu + nv].copy_(l.weight_v)
+                l._buffers["weight_u"] = self.uv[off:off + nu]
+                l._buffers["weight_v"] = self.uv[off + nu:off + nu + nv]
+                self.uv_off.append((off, off + nu))
+                off += nu + nv
+        self.dims = [(l.weight_orig.shape[0], l.weight_orig.numel() // l.weight_orig.shape[0]) for l in layers]
+        self.scr_off, off = [], 0
+        for r, c2 in self.dims:
+            self.scr_off.append(off)
+            off += int(lib().ipr_sn_scratch_floats(r, c2))
+        self.scratch_floats = off
+
+    def uv_valid(self, layers):
+        base = self.uv.data_ptr()
+        return all(l.weight_u.data_ptr() == base + 4 * o[0] for l, o in zip(layers, self.uv_off))
 
     def perm_on(self, device):
         key = str(device)
@@ -202,15 +291,25 @@ class DisPlans(object):
             self._perm_dev[key] = self.perm.to(device)
         return self._perm_dev[key]
 
-    def pack_first(self, w):
-        # B[n = co][k = (kh*3+kw)*3 + ci] = W[co, ci, kh, kw]
-        m = torch.zeros(1, 64, 64, device=w.device, dtype=torch.bfloat16)
-        m[0, :, :27] = w.permute(0, 2, 3, 1).reshape(64, 27).to(torch.bfloat16)
-        return m
+    def sn_table(self, layers, uv, sigma, grads=None):
+        arr = (SnLayer * 8)()
+        for i, l in enumerate(layers):
+            arr[i].w = l.weight_orig.data_ptr()
+            arr[i].u = uv.data_ptr() + 4 * self.uv_off[i][0]
+            arr[i].v = uv.data_ptr() + 4 * self.uv_off[i][1]
+            arr[i].sigma = sigma.data_ptr() + 4 * i
+            arr[i].grad = grads[i].data_ptr() if grads is not None else None
+            arr[i].rows, arr[i].cols = self.dims[i]
+            arr[i].scratch_off = self.scr_off[i]
+        return arr
 
 
 def _plans(module, cls):
     p = getattr(module, "_ipr_plans", None)
+    if p is not None:
+        first = next(module.parameters())
+        if p.packs.arena is not flat.arena_of(first) or (cls is DisPlans and not p.uv_valid(_sn_layers(module))):
+            p = None                                # parameters / buffers were re-created (e.g. .to(device)): rebuild
     if p is None:
         p = cls(module)
         object.__setattr__(module, "_ipr_plans", p)
@@ -225,20 +324,17 @@ class _GeneratorFn(torch.autograd.Function):
         B = z.shape[0]
         mg = P.mg
         bns = [module.convs[i][1] for i in range(3)]
-        cts = (w1, w2, w3)
         a0 = z.detach().to(torch.bfloat16).contiguous().view(B, 1, 1, -1)
         perm = P.perm_on(z.device)
-        fcp = P.packs.get("fc", fc_w, lambda w: P.fc.pack(w, perm))
-        fcb = P.packs.get("fcb", fc_b, lambda b: b[perm].contiguous())
-        h, _ = P.fc.run(a0, fcp, epi=dense.EPI_BIAS_LRELU, slope=0.0, bias=fcb)
+        fcb = fc_b.detach()[perm]
+        h, _ = P.fc.run(a0, P.packs.get("fc"), epi=dense.EPI_BIAS_LRELU, slope=0.0, bias=fcb)
         acts = [h.view(B, mg, mg, 512)]
         raws, means, rstds = [], [], []
         ctx.eval_stats = False
         for i in range(3):
-            wp = P.packs.get("ct%d" % i, cts[i], P.ct[i].pack)
             bn = bns[i]
             batch_stats = bn.training or not bn.track_running_stats or bn.running_mean is None
-            raw, stats = P.ct[i].run(acts[-1], wp, want_stats=batch_stats)
+            raw, stats = P.ct[i].run(acts[-1], P.packs.get("ct%d" % i), want_stats=batch_stats)
             if batch_stats:
                 count = raw.numel() // raw.shape[-1]
                 update = bn.training and bn.track_running_stats
@@ -248,13 +344,12 @@ class _GeneratorFn(torch.autograd.Function):
                 mean = bn.running_mean
                 scale = bn.weight.detach() * rstd
                 shift = bn.bias.detach() - mean * scale
+                ctx.eval_stats = True
             acts.append(bn_apply_relu(raw, scale, shift))
             raws.append(raw)
             means.append(mean)
             rstds.append(rstd)
-            ctx.eval_stats = not batch_stats
-        w4p = P.packs.get("ct3", w4, P.last.pack)
-        out, _ = P.last.run(acts[-1], w4p, epi=dense.EPI_TANH_NCHW, n_valid=3)
+        out, _ = P.last.run(acts[-1], P.packs.get("ct3"), epi=dense.EPI_TANH_NCHW, n_valid=3)
         ctx.module = module
         ctx.save_for_backward(a0, out, fc_w, w1, w2, w3, w4, g1, g2, g3, *acts, *raws, *means, *rstds)
         return out
@@ -275,8 +370,7 @@ class _GeneratorFn(torch.autograd.Function):
         col = im2col3(dout.contiguous(), out)
         dw4 = torch.empty_like(w4)
         P.last_wg.run(acts[3], col, dw4)
-        w4d = P.packs.get("ct3_dg", w4, P.pack_last_dgrad)
-        d_act, _ = P.last_dg.run(col, w4d)
+        d_act, _ = P.last_dg.run(col, P.packs.get("ct3_dg"))
         dws, dgs, dbs = [None] * 3, [None] * 3, [None] * 3
         sign_hook = getattr(module, "_ipr_sign_hook", None)
         for i in (2, 1, 0):
@@ -288,7 +382,7 @@ class _GeneratorFn(torch.autograd.Function):
             dx = bn_relu_bwd(d_act, raws[i], acts[i + 1], gammas[i], means[i], rstds[i], dgs[i], dbs[i], False, sg, g0, sc)
             dws[i] = torch.empty_like(cts[i])
             P.ct_wg[i].run(dx, acts[i], dws[i])
-            wd = P.packs.get("ct%d_dg" % i, cts[i], P.ct_dg[i].pack)
+            wd = P.packs.get("ct%d_dg" % i)
             if i > 0:
                 d_act, _ = P.ct_dg[i].run(dx, wd)
             else:  # into the Linear's ReLU
@@ -298,7 +392,7 @@ class _GeneratorFn(torch.autograd.Function):
         P.fc_wg.run(dh, a0, dfc_w)
         perm = P.perm_on(dev)
         dfc_b = torch.empty(fc_w.shape[0], device=dev, dtype=torch.float32)
-        dfc_b[perm] = dh.view(B, -1).float().sum(0)
+        dfc_b[perm] = colsum_bf16(dh.view(B, -1))
         return (None, None, dfc_w, dfc_b, dws[0], dgs[0], dbs[0], dws[1], dgs[1], dbs[1], dws[2], dgs[2], dbs[2], dw4)
 
 
@@ -317,22 +411,6 @@ def _sn_layers(module):
     return [net[0][0], net[0][2], net[1][0], net[1][2], net[2][0], net[2][2], net[3], net[6]]
 
 
-def _power_iteration(layer, training, eps=1e-12):
-    """torch.nn.utils.spectral_norm (legacy hook) semantics: one iteration per training forward, in place on the
-    u / v buffers; sigma = u . (W v) with the updated vectors.  Returns (sigma 0-dim, u, v) detached."""
-    w = layer.weight_orig.detach()
-    mat = w.reshape(w.shape[0], -1)
-    u, v = layer.weight_u, layer.weight_v
-    with torch.no_grad():
-        if training:
-            nv = torch.mv(mat.t(), u)
-            v.copy_(nv / nv.norm().clamp_min(eps))
-            nu = torch.mv(mat, v)
-            u.copy_(nu / nu.norm().clamp_min(eps))
-        sigma = torch.dot(u, torch.mv(mat, v))
-    return sigma, u.clone(), v.clone()
-
-
 class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, param_grads, x, *params):
@@ -340,75 +418,75 @@ class _DiscriminatorFn(torch.autograd.Function):
         layers = _sn_layers(module)
         ws, bs = params[0::2], params[1::2]
         B = x.shape[0]
-        sig = [_power_iteration(l, module.training) for l in layers]
-        xin = x.detach().contiguous()
-        col = im2col3(xin)
-        w1p = P.packs.get("c0", ws[0], P.pack_first)
-        a, _ = P.first.run(col, w1p, epi=dense.EPI_BIAS_LRELU, slope=0.1, sigma=sig[0][0], bias=bs[0].detach())
+        dev = x.device
+        # spectral norm: one batched power iteration (training) / sigma evaluation (eval) for all 8 layers, in place
+        # on the module's weight_u / weight_v buffers, then ONE copy snapshots the vectors for backward
+        sigma = torch.empty(8, device=dev, dtype=torch.float32)
+        scratch = torch.empty(P.scratch_floats, device=dev, dtype=torch.float32)
+        check(lib().ipr_sn_power_iter_f32(P.sn_table(layers, P.uv, sigma), 8, int(module.training), 1e-12,
+                                          _p(scratch), _st()), "ipr_sn_power_iter_f32")
+        uv = P.uv.clone()
+        sig = [sigma[i:i + 1] for i in range(8)]
+        col = im2col3(x.detach().contiguous())
+        a, _ = P.first.run(col, P.packs.get("c0"), epi=dense.EPI_BIAS_LRELU, slope=0.1, sigma=sig[0], bias=bs[0].detach())
         acts = [a]
         for i, plan in enumerate(P.conv):
-            wp = P.packs.get("c%d" % (i + 1), ws[i + 1], plan.pack)
-            a, _ = plan.run(acts[-1], wp, epi=dense.EPI_BIAS_LRELU, slope=0.1, sigma=sig[i + 1][0], bias=bs[i + 1].detach())
+            a, _ = plan.run(acts[-1], P.packs.get("c%d" % (i + 1)), epi=dense.EPI_BIAS_LRELU, slope=0.1, sigma=sig[i + 1],
+                            bias=bs[i + 1].detach())
             acts.append(a)
-        perm = P.perm_on(x.device)
-        w8 = P.packs.get("fcw", ws[7], lambda w: w.reshape(-1)[perm].contiguous())
-        logits = dfc_fwd(acts[-1].view(B, -1), w8, sig[7][0], bs[7].detach())
+        perm = P.perm_on(dev)
+        w8 = ws[7].detach().reshape(-1)[perm]
+        logits = dfc_fwd(acts[-1].view(B, -1), w8, sig[7], bs[7].detach())
         ctx.module, ctx.param_grads = module, param_grads
         ctx.x_needs_grad = x.requires_grad
-        flat = [t for s in sig for t in s]
-        ctx.save_for_backward(col, w8, *ws, *acts, *flat)
+        ctx.save_for_backward(col, w8, sigma, uv, *ws, *acts)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         module = ctx.module
         P = _plans(module, DisPlans)
+        layers = _sn_layers(module)
         sv = ctx.saved_tensors
-        col, w8 = sv[0], sv[1]
-        ws, acts = sv[2:10], sv[10:17]
-        flat = sv[17:]
-        sig = [flat[3 * i:3 * i + 3] for i in range(8)]
+        col, w8, sigma, uv = sv[:4]
+        ws, acts = sv[4:12], sv[12:19]
+        sig = [sigma[i:i + 1] for i in range(8)]
         want = ctx.param_grads
         B = col.shape[0]
         dev = col.device
         dlogits = dlogits.contiguous().float()
         gW, gB = [None] * 8, [None] * 8
-
-        def sn_correct(G, i):
-            # d/dW_orig of W_orig / sigma(W_orig), sigma = u^T W v  (u, v constants):  (G - <G, W_sn> u v^T) / sigma
-            sigma, u, v = sig[i]
-            W = ws[i]
-            Gm = G.reshape(G.shape[0], -1)
-            inner = (Gm * W.reshape(W.shape[0], -1)).sum() / sigma
-            return ((Gm - inner * torch.outer(u, v)) / sigma).reshape(W.shape)
-
         a7 = acts[-1].view(B, -1)
-        dy, dw8 = dfc_bwd(a7, w8, sig[7][0], dlogits, want, 0.1)
+        dy, dw8 = dfc_bwd(a7, w8, sig[7], dlogits, want, 0.1)
         if want:
             perm = P.perm_on(dev)
             g8 = torch.empty_like(dw8)
             g8[perm] = dw8
-            gW[7] = sn_correct(g8.view(1, -1), 7)
+            gW[7] = g8.view(1, -1)
             gB[7] = dlogits.sum().view(1)
         dy = dy.view(acts[-1].shape)
+        if want:
+            gB[6] = colsum_bf16(dy.view(-1, dy.shape[-1]))
         for i in range(5, -1, -1):                 # conv layers 7..2 (index i+1 in the layer list)
             li = i + 1
             if want:
-                gB[li] = dy.float().sum((0, 1, 2))
-                G = torch.empty_like(ws[li])
-                P.conv_wg[i].run(dy, acts[i], G)
-                gW[li] = sn_correct(G, li)
-            wd = P.packs.get("c%d_dg" % li, ws[li], P.conv_dg[i].pack)
-            dy, _ = P.conv_dg[i].run(dy, wd, epi=dense.EPI_MASK, slope=0.1, mask=acts[i], sigma=sig[li][0])
-        if want:
-            gB[0] = dy.float().sum((0, 1, 2))
-            G = torch.empty_like(ws[0])
-            P.first_wg.run(dy, col, G)
-            gW[0] = sn_correct(G, 0)
+                gW[li] = torch.empty_like(ws[li])
+                P.conv_wg[i].run(dy, acts[i], gW[li])
+            # the data-gradient GEMM's epilogue also yields the column sums of its output = the bias gradient below
+            dy, st = P.conv_dg[i].run(dy, P.packs.get("c%d_dg" % li), epi=dense.EPI_MASK, slope=0.1, mask=acts[i],
+                                      sigma=sig[li], want_stats=want)
+            if want:
+                gB[i] = colsum_partials(st)[:dy.shape[-1]]
         dx = None
         if ctx.x_needs_grad:
-            wd = P.packs.get("c0_dg", ws[0], P.first_dg.pack)
-            dx, _ = P.first_dg.run(dy, wd, epi=dense.EPI_LINEAR_NCHW, sigma=sig[0][0], n_valid=3)
+            dx, _ = P.first_dg.run(dy, P.packs.get("c0_dg"), epi=dense.EPI_LINEAR_NCHW, sigma=sig[0], n_valid=3)
+        if want:
+            gW[0] = torch.empty_like(ws[0])
+            P.first_wg.run(dy, col, gW[0])
+            # gradients so far are w.r.t. W / sigma: one batched kernel pair turns them into d/dW_orig
+            scratch = torch.empty(P.scratch_floats, device=dev, dtype=torch.float32)
+            check(lib().ipr_sn_weight_grad_f32(P.sn_table(layers, uv, sigma, gW), 8, _p(scratch), _st()),
+                  "ipr_sn_weight_grad_f32")
         grads = []
         for i in range(8):
             grads += [gW[i], gB[i]]

@@ -1,0 +1,67 @@
+"""Flat fp32 arenas for a network's parameters and gradients.
+
+``arena_for(params)`` re-points every parameter's ``.data`` (and ``.grad``) into one contiguous buffer, each
+tensor 16-byte aligned.  That is what lets (a) Adam update a whole network in one launch, (b) all bf16 GEMM
+operand layouts be rebuilt from the masters by one gather launch, and (c) data-parallel training all-reduce a
+network's gradients with a single NCCL call on one buffer.  ``state_dict`` keys / shapes are untouched.
+"""
+import torch
+
+_BY_PARAM = {}          # id(param) -> Arena
+
+
+class Arena(object):
+    def __init__(self, params):
+        params = [p for p in params]
+        assert params and all(p.dtype == torch.float32 for p in params)
+        dev = params[0].device
+        assert all(p.device == dev for p in params)
+        self.params = params
+        self.offsets = []
+        off = 0
+        for p in params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4                      # keep every tensor 16-byte aligned
+        self.numel = max(off, 4)
+        self.param = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        self.version = 0                                          # bumped by whoever rewrites the masters
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets):
+                n = p.numel()
+                self.param[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.param[o:o + n].view(p.shape)
+                p.grad = self.grad[o:o + n].view(p.shape)
+                _BY_PARAM[id(p)] = self
+        self.index = {id(p): o for p, o in zip(params, self.offsets)}
+
+    def valid(self):
+        base, end = self.param.data_ptr(), self.param.data_ptr() + self.numel * 4
+        return all(base <= p.data_ptr() < end for p in self.params)
+
+    def offset_of(self, p):
+        return self.index[id(p)]
+
+    def bind_grads(self):
+        """(Re-)attach ``.grad`` views (after something set them to None)."""
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + o * 4:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self):
+        self.grad.zero_()
+        self.bind_grads()
+
+
+def arena_for(params):
+    """The arena holding exactly these parameters (created on first use)."""
+    params = list(params)
+    hit = _BY_PARAM.get(id(params[0]))
+    if hit is not None and hit.valid() and len(hit.params) == len(params) and all(a is b for a, b in zip(hit.params, params)):
+        return hit
+    return Arena(params)
+
+
+def arena_of(param):
+    hit = _BY_PARAM.get(id(param))
+    return hit if hit is not None and hit.valid() else None

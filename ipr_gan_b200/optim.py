@@ -1,0 +1,76 @@
+"""``FlatAdam``: ``torch.optim.Adam`` whose ``step()`` is one sm_100a launch over the network's flat arenas
+(csrc/optim.cu).  It IS a ``torch.optim.Adam`` (same ``param_groups`` / ``state_dict`` format, so checkpoints
+written by the reference load and vice versa), only the arithmetic moved.
+
+With ``torch.distributed`` initialised (one process per GPU) ``step()`` first all-reduces the gradient arena over
+NCCL -- one call per network per step -- and divides by the world size: the reference's ``nn.DataParallel``
+gradient reduction (experiments/base.py:36-39) without the per-forward parameter broadcast.
+"""
+import ctypes
+
+import torch
+
+from . import flat
+from ._lib import check, lib
+
+
+class FlatAdam(torch.optim.Adam):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, **ignored):
+        if amsgrad:
+            raise NotImplementedError("FlatAdam: amsgrad is not on the IPR-GAN path")
+        params = list(params)
+        super().__init__(params, lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        if len(self.param_groups) != 1:
+            raise NotImplementedError("FlatAdam: a single parameter group is expected")
+        self.arena = flat.arena_for(params)
+        dev = self.arena.param.device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdam needs CUDA parameters (no CPU fallback)")
+        self._m = torch.zeros_like(self.arena.param)
+        self._v = torch.zeros_like(self.arena.param)
+        self._step = torch.zeros((), device=dev, dtype=torch.float32)
+        self._bind_state()
+
+    def _bind_state(self):
+        for p, o in zip(self.arena.params, self.arena.offsets):
+            n = p.numel()
+            self.state[p] = {"step": self._step, "exp_avg": self._m[o:o + n].view(p.shape),
+                             "exp_avg_sq": self._v[o:o + n].view(p.shape)}
+
+    def zero_grad(self, set_to_none=True):
+        self.arena.zero_grad()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        with torch.no_grad():
+            step = None
+            for p, o in zip(self.arena.params, self.arena.offsets):
+                st = self.state.get(p)
+                if st:
+                    n = p.numel()
+                    self._m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    self._v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    step = st["step"]
+            if step is not None:
+                self._step.fill_(float(step))
+        self._bind_state()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        g = self.param_groups[0]
+        arena = self.arena
+        arena.bind_grads()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1:
+                torch.distributed.all_reduce(arena.grad)
+                arena.grad.mul_(1.0 / world)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(lib().ipr_adam_flat_f32(ctypes.c_void_p(arena.param.data_ptr()), ctypes.c_void_p(arena.grad.data_ptr()),
+                                      ctypes.c_void_p(self._m.data_ptr()), ctypes.c_void_p(self._v.data_ptr()),
+                                      arena.numel, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                      float(g["eps"]), float(g["weight_decay"]),
+                                      ctypes.c_void_p(self._step.data_ptr()), st), "ipr_adam_flat_f32")
+        arena.version += 1
+        return loss
