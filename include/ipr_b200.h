@@ -228,11 +228,12 @@ size_t ipr_wgrad_workspace_bytes(const ipr_wgrad_t *d_host);
 int    ipr_wgrad_total_kblocks(const ipr_wgrad_t *d_host);     /* 64-pixel blocks of the reduction */
 int    ipr_wgrad_bf16(const ipr_wgrad_t *d_host, ipr_stream_t stream);
 
-/* grad[row(n)*s_n + col_off[p][k]] (+)= scale * sum_splits ws[split][p][n][k]   (col_off < 0: skipped;
- * row(n) = row_map ? row_map[n] : n).  Adds the splits in a fixed order and scatters from the GEMM layout
- * into the parameter's own layout ((O,I,kh,kw), (I,O,kh,kw) or (O,I)). */
+/* For every output row n:  grad[row(n)*s_n + out_pos[j]] (+)= scale * sum_splits ws[split][src_idx[j] / k_total][n][src_idx[j] % k_total]
+ * for j < n_out, out_pos ascending (row(n) = row_map ? row_map[n] : n).  Adds the splits in a fixed order and permutes
+ * the GEMM layout into the parameter's own layout ((O,I,kh,kw), (I,O,kh,kw) or (O,I)) with coalesced reads and writes. */
 int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_rows, int k_total,
-                         const int32_t *col_off, const int32_t *row_map, int64_t s_n, float *grad,
+                         const int32_t *src_idx, const int32_t *out_pos, int n_out,
+                         const int32_t *row_map, int64_t s_n, float *grad,
                          int accumulate, float scale, ipr_stream_t stream);
 
 /* ------------------------------------------------------------------ memory-bound layers around the GEMMs */
@@ -293,6 +294,7 @@ typedef struct {
     float *u, *v;          /* power-iteration vectors (weight_u: rows, weight_v: cols), updated in place     */
     float *sigma;          /* device scalar written by the power iteration, read by the weight gradient     */
     float *grad;           /* ipr_sn_weight_grad_f32: gradient w.r.t. W/sigma in, w.r.t. W out (in place)   */
+    float *grad_out;       /* optional: if not NULL the result is ADDED here instead (e.g. the .grad arena)   */
     int32_t rows, cols;
     int64_t scratch_off;   /* offset (floats) of this layer's private slice of `scratch`,
                               at least ipr_sn_scratch_floats(rows, cols) long                               */

@@ -20,7 +20,7 @@ SIGN_MAX_LAYERS = 64
 
 class SnLayer(ctypes.Structure):
     """ipr_sn_layer_t"""
-    _fields_ = [("w", c_ptr), ("u", c_ptr), ("v", c_ptr), ("sigma", c_ptr), ("grad", c_ptr),
+    _fields_ = [("w", c_ptr), ("u", c_ptr), ("v", c_ptr), ("sigma", c_ptr), ("grad", c_ptr), ("grad_out", c_ptr),
                 ("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("scratch_off", ctypes.c_int64)]
 
 
@@ -72,7 +72,7 @@ SIGNATURES = {
     "ipr_sn_weight_grad_f32": (c_int, [c_ptr, c_int, c_ptr, c_ptr]),
     "ipr_adam_flat_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_ptr, c_ptr]),
     "ipr_gather_pack_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
-    "ipr_wgrad_reduce_f32": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_int, c_f32, c_ptr]),
+    "ipr_wgrad_reduce_f32": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_int, c_f32, c_ptr]),
 }
 
 _lib = None

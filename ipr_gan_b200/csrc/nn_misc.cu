@@ -184,10 +184,16 @@ bn_bwd_finalize_kernel(const float *__restrict__ partial, int rows, int C, doubl
                        const float *__restrict__ sign, float gamma0, float sign_scale,
                        float *__restrict__ coef)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ double s1[8][33], s2[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     double sg = 0.0, sx = 0.0;
-    for (int r = 0; r < rows; r++) { sg += (double)partial[(size_t)r * 2 * C + c]; sx += (double)partial[(size_t)r * 2 * C + C + c]; }
+    if (c < C)
+        for (int r = ty; r < rows; r += 8) { sg += (double)partial[(size_t)r * 2 * C + c]; sx += (double)partial[(size_t)r * 2 * C + C + c]; }
+    s1[ty][tx] = sg; s2[ty][tx] = sx;
+    __syncthreads();
+    if (ty != 0 || c >= C) return;
+    for (int y = 1; y < 8; y++) { sg += s1[y][tx]; sx += s2[y][tx]; }
     const float g = gamma[c], rs = rstd[c], mu = mean[c];
     float dg = (float)sx;
     const float a = g * rs;
@@ -196,8 +202,8 @@ bn_bwd_finalize_kernel(const float *__restrict__ partial, int rows, int C, doubl
     coef[C + c] = b;
     coef[2 * C + c] = -a * (float)(sg / count) - b * mu;
     if (sign) {                                      // d/dgamma of mean_c relu(gamma0 - gamma*sign)
-        const float s = sign[c];
-        if (gamma0 - g * s > 0.0f) dg += -s * sign_scale / (float)C;
+        const float sv = sign[c];
+        if (gamma0 - g * sv > 0.0f) dg += -sv * sign_scale / (float)C;
     }
     dgamma[c] = accumulate ? dgamma[c] + dg : dg;
     dbeta[c] = accumulate ? dbeta[c] + (float)sg : (float)sg;
@@ -265,16 +271,24 @@ dfc_bwd_data_kernel(const uint4 *__restrict__ a, const float *__restrict__ w, co
     }
 }
 
-// dw[k] (+)= sum_b dlogit[b] * a[b,k]   (w.r.t. the normalised weight);  one thread per k, fixed order over b
+// dw[k] (+)= sum_b dlogit[b] * a[b,k]   (w.r.t. the normalised weight); CTA = 32 columns x 8 batch lanes, fixed order
 __global__ void __launch_bounds__(256)
 dfc_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ dlogit, float *__restrict__ dw,
                       int batch, int K, int accumulate)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + tx;
     float acc = 0.0f;
-    for (int b = 0; b < batch; b++) acc += __ldg(dlogit + b) * __bfloat162float(a[(size_t)b * K + k]);
-    dw[k] = accumulate ? dw[k] + acc : acc;
+    if (k < K)
+        for (int b = ty; b < batch; b += 8) acc += __ldg(dlogit + b) * __bfloat162float(a[(size_t)b * K + k]);
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && k < K) {
+#pragma unroll
+        for (int y = 1; y < 8; y++) acc += sm[y][tx];
+        dw[k] = accumulate ? dw[k] + acc : acc;
+    }
 }
 
 inline unsigned grid_1d(long long items, int threads, int waves = 8) {
@@ -361,7 +375,7 @@ extern "C" int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const void
     bn_bwd_reduce_kernel<<<(unsigned)ctas, 256, smem, st>>>((const uint4 *)dy, (const uint4 *)xraw, (const uint4 *)act,
                                                             mean, rstd, rows, c_vec, partial);
     IPR_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<(channels + 255) / 256, 256, 0, st>>>(partial, (int)ctas, channels, (double)rows, gamma, mean,
+    bn_bwd_finalize_kernel<<<(channels + 31) / 32, 256, 0, st>>>(partial, (int)ctas, channels, (double)rows, gamma, mean,
                                                                   rstd, dgamma, dbeta, accumulate, sign, gamma0,
                                                                   sign_scale, coef);
     IPR_LAUNCH_CHECK();
@@ -395,7 +409,7 @@ extern "C" int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigm
                                                                         n_vec, k / 8, slope);
     IPR_LAUNCH_CHECK();
     if (dw) {
-        dfc_bwd_weight_kernel<<<(k + 255) / 256, 256, 0, ipr_cu(stream)>>>((const __nv_bfloat16 *)a, dlogit, dw, batch, k,
+        dfc_bwd_weight_kernel<<<(k + 31) / 32, 256, 0, ipr_cu(stream)>>>((const __nv_bfloat16 *)a, dlogit, dw, batch, k,
                                                                          accumulate_dw);
         IPR_LAUNCH_CHECK();
     }
@@ -405,15 +419,24 @@ extern "C" int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigm
 // ------------------------------------------------------------------------------------ column reductions
 namespace {
 
-// stage 1: out[g][c] = sum_{r = g, g+G, ...} in[r][c]      (fp32 partial rows, e.g. GEMM-epilogue statistics)
+// stage 1: out[g][c] = sum over the rows assigned to group g of in[r][c]   (fp32 partial rows, e.g. GEMM-epilogue
+// statistics).  CTA = 32 columns x 8 row lanes; grid = (ncols/32, G).
 __global__ void __launch_bounds__(256)
 colsum_partials_stage1(const float *__restrict__ in, int rows, int ncols, float *__restrict__ out)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float acc = 0.0f;
-    for (int r = blockIdx.y; r < rows; r += gridDim.y) acc += in[(size_t)r * ncols + c];
-    out[(size_t)blockIdx.y * ncols + c] = acc;
+    if (c < ncols)
+        for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) acc += in[(size_t)r * ncols + c];
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < ncols) {
+#pragma unroll
+        for (int y = 1; y < 8; y++) acc += sm[y][tx];
+        out[(size_t)blockIdx.y * ncols + c] = acc;
+    }
 }
 // stage 2: out[c] (+)= scale * sum_g in[g][c], double accumulation, fixed order
 __global__ void __launch_bounds__(256)
@@ -457,8 +480,8 @@ extern "C" int ipr_colsum_partials_f32(const float *partial, int rows, int ncols
     IPR_REQUIRE(partial && out && workspace, IPR_E_NULL);
     IPR_REQUIRE(rows > 0 && ncols > 0, IPR_E_SHAPE);
     IPR_REQUIRE(workspace_bytes >= ipr_colsum_workspace_bytes(ncols), IPR_E_WORKSPACE);
-    const int G = rows < 64 ? rows : 64;
-    dim3 grid((ncols + 255) / 256, G);
+    const int G = rows < 8 * 64 ? (rows + 7) / 8 : 64;
+    dim3 grid((ncols + 31) / 32, G);
     colsum_partials_stage1<<<grid, 256, 0, ipr_cu(stream)>>>(partial, rows, ncols, (float *)workspace);
     IPR_LAUNCH_CHECK();
     colsum_stage2<<<(ncols + 255) / 256, 256, 0, ipr_cu(stream)>>>((const float *)workspace, G, ncols, out, accumulate, scale);

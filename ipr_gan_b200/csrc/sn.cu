@@ -59,20 +59,27 @@ sn_v_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scrat
     for (int c = threadIdx.x; c < L.cols; c += blockDim.x) L.v[c] *= inv;
 }
 
-// B1: s[row] = W[row,:] . v     (one warp per row)
+// B1: s[row] = W[row,:] . v     (one CTA per row, 128-bit loads where the row is 16-byte aligned)
 __global__ void __launch_bounds__(256)
 sn_wv_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
 {
+    __shared__ float red[32];
     const int l = find_layer(tab, blockIdx.x);
     const ipr_sn_layer_t L = tab.layer[l];
-    const int row = (blockIdx.x - tab.cta_begin[l]) * 8 + (threadIdx.x >> 5);
-    if (row >= L.rows) return;
-    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x - tab.cta_begin[l];
     const float *w = L.w + (size_t)row * L.cols;
     float acc = 0.0f;
-    for (int c = lane; c < L.cols; c += 32) acc += w[c] * L.v[c];
-    acc = ipr_warp_sum(acc);
-    if (lane == 0) scratch[L.scratch_off + row] = acc;
+    if ((L.cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(L.v)) & 15) == 0) {
+        const float4 *w4 = reinterpret_cast<const float4 *>(w), *v4 = reinterpret_cast<const float4 *>(L.v);
+        for (int c = threadIdx.x; c < (L.cols >> 2); c += blockDim.x) {
+            const float4 a = w4[c], b = v4[c];
+            acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+    } else {
+        for (int c = threadIdx.x; c < L.cols; c += blockDim.x) acc += w[c] * L.v[c];
+    }
+    const float tot = ipr_block_sum(acc, red);
+    if (threadIdx.x == 0) scratch[L.scratch_off + row] = tot;
 }
 
 // B2 (one CTA per layer): update: u = s / max(||s||, eps), sigma = u . s ; no update: sigma = u_old . s
@@ -126,7 +133,8 @@ sn_grad_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ sc
     const long long i = (long long)(blockIdx.x - tab.cta_begin[l]) * 256 + threadIdx.x;
     if (i >= n) return;
     const int r = (int)(i / L.cols), c = (int)(i - (long long)r * L.cols);
-    L.grad[i] = (L.grad[i] - coef * L.u[r] * L.v[c]) * inv;
+    const float out = (L.grad[i] - coef * L.u[r] * L.v[c]) * inv;
+    if (L.grad_out) L.grad_out[i] += out; else L.grad[i] = out;
 }
 
 int fill(SnTable &t, const ipr_sn_layer_t *layers, int n)
@@ -172,7 +180,7 @@ extern "C" int ipr_sn_power_iter_f32(const ipr_sn_layer_t *layers_host, int n_la
         IPR_LAUNCH_CHECK();
     }
     int total = 0;
-    for (int i = 0; i < n_layers; i++) { t.cta_begin[i] = total; total += (t.layer[i].rows + 7) / 8; }
+    for (int i = 0; i < n_layers; i++) { t.cta_begin[i] = total; total += t.layer[i].rows; }
     t.cta_begin[n_layers] = total;
     sn_wv_kernel<<<total, 256, 0, st>>>(t, scratch);
     IPR_LAUNCH_CHECK();

@@ -149,28 +149,31 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// grad[n*s_n + col_off[p][k]] (+)= scale * sum_splits ws[split][p][n][k]      (fixed summation order)
+// One CTA per output row n: sum the splits of ws[.][p][n][k] into shared memory (coalesced reads, fixed order),
+// then write grad[row(n)*s_n + out_pos[j]] (+)= scale * smem[src_idx[j]] for j in ascending address order
+// (coalesced writes): the GEMM layout [tap][c] is permuted into the parameter's own layout on the way out.
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int phases, int n_rows, int n_pad, int k_total,
-                    const int *__restrict__ col_off, const int *__restrict__ row_map, long long s_n,
-                    float *__restrict__ grad, int accumulate, float scale)
+wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int phases, int n_pad, int k_total,
+                    const int *__restrict__ src_idx, const int *__restrict__ out_pos, int n_out,
+                    const int *__restrict__ row_map, long long s_n, float *__restrict__ grad, int accumulate, float scale)
 {
-    const long long total = (long long)phases * n_rows * k_total;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    extern __shared__ float sm[];
+    const int n = blockIdx.x;
     const size_t split_stride = (size_t)phases * n_pad * k_total;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int k = (int)(e % k_total);
-        const long long t = e / k_total;
-        const int n = (int)(t % n_rows);
-        const int ph = (int)(t / n_rows);
-        const int off = __ldg(col_off + (size_t)ph * k_total + k);
-        if (off < 0) continue;
+    for (int e = threadIdx.x; e < phases * k_total; e += blockDim.x) {
+        const int ph = e / k_total, k = e - ph * k_total;
         const float *src = ws + ((size_t)ph * n_pad + n) * k_total + k;
         float acc = 0.0f;
         for (int s = 0; s < splits; s++) acc += src[s * split_stride];
-        const int rn = row_map ? __ldg(row_map + n) : n;
-        float *dst = grad + (size_t)rn * s_n + off;
-        *dst = accumulate ? *dst + acc * scale : acc * scale;
+        sm[e] = acc * scale;
+    }
+    __syncthreads();
+    const int rn = row_map ? __ldg(row_map + n) : n;
+    float *dst = grad + (size_t)rn * s_n;
+    for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
+        const float v = sm[__ldg(src_idx + j)];
+        const int o = __ldg(out_pos + j);
+        dst[o] = accumulate ? dst[o] + v : v;
     }
 }
 
@@ -283,18 +286,24 @@ extern "C" int ipr_wgrad_bf16(const ipr_wgrad_t *d, ipr_stream_t stream)
 }
 
 extern "C" int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_rows, int k_total,
-                                    const int32_t *col_off, const int32_t *row_map, int64_t s_n, float *grad,
+                                    const int32_t *src_idx, const int32_t *out_pos, int n_out,
+                                    const int32_t *row_map, int64_t s_n, float *grad,
                                     int accumulate, float scale, ipr_stream_t stream)
 {
-    IPR_REQUIRE(workspace && col_off && grad, IPR_E_NULL);
-    IPR_REQUIRE(splits > 0 && phases > 0 && n_rows > 0 && k_total > 0, IPR_E_SHAPE);
+    IPR_REQUIRE(workspace && src_idx && out_pos && grad, IPR_E_NULL);
+    IPR_REQUIRE(splits > 0 && phases > 0 && n_rows > 0 && k_total > 0 && n_out > 0, IPR_E_SHAPE);
     const int n_pad = ((n_rows + 127) / 128) * 128;
-    const long long total = (long long)phases * n_rows * k_total;
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)ipr_sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, ipr_cu(stream)>>>(workspace, splits, phases, n_rows, n_pad, k_total,
-                                                                     col_off, row_map, (long long)s_n, grad, accumulate, scale);
+    const size_t smem = (size_t)phases * k_total * sizeof(float);
+    IPR_REQUIRE(smem <= 160 * 1024, IPR_E_UNSUPPORTED);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    wgrad_reduce_kernel<<<(unsigned)n_rows, 256, smem, ipr_cu(stream)>>>(workspace, splits, phases, n_pad, k_total, src_idx,
+                                                                       out_pos, n_out, row_map, (long long)s_n, grad,
+                                                                       accumulate, scale);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

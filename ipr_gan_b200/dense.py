@@ -248,14 +248,19 @@ class WGradPlan(object):
                         else:                      # (O, I, kh, kw): n = O (stride I*k*k), c = I (stride k*k)
                             col_off[ph, t * self.x_c:(t + 1) * self.x_c] = c * (ksz * ksz) + kh * ksz + kw
                 s_n = ksz * ksz if k == "convT4s2" else weight_shape[1] * ksz * ksz
-        self.col_off_host, self.s_n = col_off.contiguous(), int(s_n)
+        self.s_n = int(s_n)
+        flat_off = col_off.reshape(-1).to(torch.int64)
+        src = torch.nonzero(flat_off >= 0).reshape(-1)
+        order = torch.argsort(flat_off[src], stable=True)
+        self.src_idx_host = src[order].to(torch.int32).contiguous()          # phase * k_total + k
+        self.out_pos_host = flat_off[src][order].to(torch.int32).contiguous()   # ascending offsets inside a row
         self._dev = {}
 
     def _tables(self, device):
         key = str(device)
         if key not in self._dev:
             rp = self.row_perm.to(device=device, dtype=torch.int32).contiguous() if self.row_perm is not None else None
-            self._dev[key] = (self.col_off_host.to(device), rp)
+            self._dev[key] = (self.src_idx_host.to(device), self.out_pos_host.to(device), rp)
         return self._dev[key]
 
     def run(self, y, x, grad, accumulate=False, scale=1.0, splits=None):
@@ -295,9 +300,10 @@ class WGradPlan(object):
         check(L.ipr_wgrad_bf16(ctypes.byref(d), st), "ipr_wgrad_bf16(%s)" % self.fwd.kind)
         _prof_end("wgrad:" + self.fwd.kind, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps *
                   getattr(self, "k_valid_override", xc) * getattr(self, "rows_valid_override", self.rows), ev)
-        col_off, row_map = self._tables(x.device)
+        src_idx, out_pos, row_map = self._tables(x.device)
         check(L.ipr_wgrad_reduce_f32(ws.data_ptr(), splits, self.n_phases, self.rows, self.k_total,
-                                     col_off.data_ptr(), row_map.data_ptr() if row_map is not None else None,
+                                     src_idx.data_ptr(), out_pos.data_ptr(), src_idx.numel(),
+                                     row_map.data_ptr() if row_map is not None else None,
                                      self.s_n, grad.data_ptr(), int(bool(accumulate)), float(scale), st),
               "ipr_wgrad_reduce_f32")
         return grad

@@ -291,9 +291,10 @@ class DisPlans(object):
             self._perm_dev[key] = self.perm.to(device)
         return self._perm_dev[key]
 
-    def sn_table(self, layers, uv, sigma, grads=None):
+    def sn_table(self, layers, uv, sigma, grads=None, grad_outs=None):
         arr = (SnLayer * 8)()
         for i, l in enumerate(layers):
+            arr[i].grad_out = grad_outs[i].data_ptr() if grad_outs is not None and grad_outs[i] is not None else None
             arr[i].w = l.weight_orig.data_ptr()
             arr[i].u = uv.data_ptr() + 4 * self.uv_off[i][0]
             arr[i].v = uv.data_ptr() + 4 * self.uv_off[i][1]
@@ -302,6 +303,17 @@ class DisPlans(object):
             arr[i].rows, arr[i].cols = self.dims[i]
             arr[i].scratch_off = self.scr_off[i]
         return arr
+
+
+def _grad_dst(param):
+    """Where a weight gradient goes: straight into the parameter's ``.grad`` arena view (accumulating, nothing is
+    returned to autograd -- saves one add kernel and one temporary per parameter) or, without an arena, a fresh tensor
+    that autograd accumulates itself.  -> (destination, accumulate, value returned from backward)"""
+    g = param.grad
+    if g is not None and g.is_contiguous() and flat.arena_of(param) is not None:
+        return g, True, None
+    t = torch.empty_like(param)
+    return t, False, t
 
 
 def _plans(module, cls):
@@ -368,32 +380,37 @@ class _GeneratorFn(torch.autograd.Function):
         dev = a0.device
         # last layer: Tanh' fused into the patch gather, then one GEMM for d(a3) and one for dW4
         col = im2col3(dout.contiguous(), out)
-        dw4 = torch.empty_like(w4)
-        P.last_wg.run(acts[3], col, dw4)
+        mod_c = module.convs
+        dw4, acc4, ret4 = _grad_dst(mod_c[3].weight)
+        P.last_wg.run(acts[3], col, dw4, accumulate=acc4)
         d_act, _ = P.last_dg.run(col, P.packs.get("ct3_dg"))
         dws, dgs, dbs = [None] * 3, [None] * 3, [None] * 3
         sign_hook = getattr(module, "_ipr_sign_hook", None)
         for i in (2, 1, 0):
-            dgs[i] = torch.empty_like(gammas[i])
-            dbs[i] = torch.empty_like(gammas[i])
+            dg_t, acc_g, dgs[i] = _grad_dst(mod_c[i][1].weight)
+            db_t, acc_b, dbs[i] = _grad_dst(mod_c[i][1].bias)
+            if acc_g != acc_b:                       # one kernel writes both: keep them in the same mode
+                dg_t = dgs[i] = torch.empty_like(gammas[i])
+                db_t = dbs[i] = torch.empty_like(gammas[i])
+                acc_g = False
             sg, g0, sc = (None, 0.0, 0.0)
             if sign_hook is not None:
                 sg, g0, sc = sign_hook(i)
-            dx = bn_relu_bwd(d_act, raws[i], acts[i + 1], gammas[i], means[i], rstds[i], dgs[i], dbs[i], False, sg, g0, sc)
-            dws[i] = torch.empty_like(cts[i])
-            P.ct_wg[i].run(dx, acts[i], dws[i])
+            dx = bn_relu_bwd(d_act, raws[i], acts[i + 1], gammas[i], means[i], rstds[i], dg_t, db_t, acc_g, sg, g0, sc)
+            dw_t, acc_w, dws[i] = _grad_dst(mod_c[i][0].weight)
+            P.ct_wg[i].run(dx, acts[i], dw_t, accumulate=acc_w)
             wd = P.packs.get("ct%d_dg" % i)
             if i > 0:
                 d_act, _ = P.ct_dg[i].run(dx, wd)
             else:  # into the Linear's ReLU
                 d_act, _ = P.ct_dg[i].run(dx, wd, epi=dense.EPI_MASK, slope=0.0, mask=acts[0])
         dh = d_act.view(B, 1, 1, -1)
-        dfc_w = torch.empty_like(fc_w)
-        P.fc_wg.run(dh, a0, dfc_w)
+        dfc_t, acc_fc, dfc_w = _grad_dst(module.fc[0].weight)
+        P.fc_wg.run(dh, a0, dfc_t, accumulate=acc_fc)
         perm = P.perm_on(dev)
         dfc_b = torch.empty(fc_w.shape[0], device=dev, dtype=torch.float32)
         dfc_b[perm] = colsum_bf16(dh.view(B, -1))
-        return (None, None, dfc_w, dfc_b, dws[0], dgs[0], dbs[0], dws[1], dgs[1], dbs[1], dws[2], dgs[2], dbs[2], dw4)
+        return (None, None, dfc_w, dfc_b, dws[0], dgs[0], dbs[0], dws[1], dgs[1], dbs[1], dws[2], dgs[2], dbs[2], ret4)
 
 
 def generator_forward(module, z):
@@ -456,6 +473,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         dev = col.device
         dlogits = dlogits.contiguous().float()
         gW, gB = [None] * 8, [None] * 8
+        gW_ret = {}
         a7 = acts[-1].view(B, -1)
         dy, dw8 = dfc_bwd(a7, w8, sig[7], dlogits, want, 0.1)
         if want:
@@ -485,11 +503,17 @@ class _DiscriminatorFn(torch.autograd.Function):
             P.first_wg.run(dy, col, gW[0])
             # gradients so far are w.r.t. W / sigma: one batched kernel pair turns them into d/dW_orig
             scratch = torch.empty(P.scratch_floats, device=dev, dtype=torch.float32)
-            check(lib().ipr_sn_weight_grad_f32(P.sn_table(layers, uv, sigma, gW), 8, _p(scratch), _st()),
+            outs = []
+            for i, l in enumerate(layers):
+                dst, acc, ret = _grad_dst(l.weight_orig)
+                outs.append(dst if acc else None)
+                if acc:
+                    gW_ret[i] = None
+            check(lib().ipr_sn_weight_grad_f32(P.sn_table(layers, uv, sigma, gW, outs), 8, _p(scratch), _st()),
                   "ipr_sn_weight_grad_f32")
         grads = []
         for i in range(8):
-            grads += [gW[i], gB[i]]
+            grads += [gW_ret[i] if (want and i in gW_ret) else gW[i], gB[i]]
         return (None, None, dx, *grads)
 
 

@@ -10,7 +10,7 @@ import ctypes
 
 import torch
 
-from . import flat
+from . import dist, flat
 from ._lib import check, lib
 
 
@@ -61,11 +61,7 @@ class FlatAdam(torch.optim.Adam):
         g = self.param_groups[0]
         arena = self.arena
         arena.bind_grads()
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            world = torch.distributed.get_world_size()
-            if world > 1:
-                torch.distributed.all_reduce(arena.grad)
-                arena.grad.mul_(1.0 / world)
+        dist.allreduce_mean_(arena.grad)            # no-op for a single process
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         check(lib().ipr_adam_flat_f32(ctypes.c_void_p(arena.param.data_ptr()), ctypes.c_void_p(arena.grad.data_ptr()),
                                       ctypes.c_void_p(self._m.data_ptr()), ctypes.c_void_p(self._v.data_ptr()),
