@@ -133,6 +133,12 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def _dbg(msg):
+    if os.environ.get("IPR_BENCH_DEBUG"):
+        sys.stderr.write("[rank %s] %s\n" % (os.environ.get("RANK", "0"), msg))
+        sys.stderr.flush()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -153,8 +159,10 @@ def run_b200(args):
     gen = torch.Generator().manual_seed(1234 + rank)
     real_h = torch.randn(local_batch, 3, 32, 32, generator=gen).clamp(-1, 1).pin_memory()
     z_h = torch.randn(local_batch, 128, generator=gen).pin_memory()
+    _dbg('trainer built')
     tr.set_inputs(real_h, z_h)
     tr.capture()
+    _dbg('captured')
     flush = torch.empty(256 * 1024 * 1024 // 4, device=device)       # 256 MiB > 126 MB of L2
 
     def barrier():
@@ -185,7 +193,9 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    _dbg('warm')
     total_ms = timed(tr.step, args.steps)
+    _dbg('timed')
     # end to end through the public call: pinned host batch in, metrics dict out, every step
     metrics_box = {}
 
@@ -197,6 +207,7 @@ def run_b200(args):
     t0 = time.perf_counter()
     e2e_ms = timed(e2e_step, args.steps)
     wall_e2e = time.perf_counter() - t0
+    _dbg('e2e done')
     clocks = sampler.stop() if rank == 0 else None
 
     # live tensor-roofline measurement: one eager step with CUDA events around every GEMM launch
@@ -234,11 +245,12 @@ def run_b200(args):
             ts.append(a.elapsed_time(b))
         ts.sort()
         return 36.0 * B * 32 * 32 / (ts[len(ts) // 2] * 1e-3) / 1e9
+    _dbg('profiled gemms')
     ssim_small, ssim_big = ssim_gbs(local_batch), ssim_gbs(16384)
+    _dbg('ssim done')
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     ms = total_ms / args.steps
     value = 1e3 / ms
@@ -282,8 +294,18 @@ def run_b200(args):
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line))
+    _finish(world)
+
+
+def _finish(world):
+    """Leave without tearing NCCL down: destroying a process group whose collectives live inside a captured CUDA
+    graph can block at exit; the ranks just synchronise and exit."""
+    import torch
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":
