@@ -182,7 +182,7 @@ typedef struct {
     int32_t q_h, q_w;              /* virtual output grid per image; q_w*q_h divides or is divided by 128 */
     const void *b;                 /* bf16 [n_phases][n_total][n_taps*a_c]                           */
     int32_t n_total;               /* padded N (multiple of block_n)                                 */
-    int32_t block_n;               /* 16, 32, 64 or 128                                              */
+    int32_t block_n;               /* 16, 32, 64, 128 or 256                                         */
     int32_t n_phases, n_taps;
     int8_t  tap_map[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
     int8_t  tap_dh[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];

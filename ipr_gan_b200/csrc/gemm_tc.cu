@@ -14,8 +14,9 @@
 // * warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2-5 epilogue
 //   (tcgen05.ld 32 lanes x 32 columns, fused 1/sigma, bias, LeakyReLU / activation-gradient mask /
 //   tanh, bf16 pack, per-column sum and sum-of-squares for BatchNorm).
-// * two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's epilogue
-//   overlaps the other's main loop.
+// * persistent: one CTA per SM walks the tile list; the accumulator is double-buffered in TMEM (2 x BLOCK_N columns)
+//   so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1, and the TMA producer never drains between
+//   tiles (6-8 smem stages, ~190 KB).
 #include "ipr_common.cuh"
 #include "tc_common.cuh"
 
@@ -31,7 +32,7 @@ constexpr int NUM_THREADS = 192;
 
 struct TgParams {
     int a_n, q_h, q_w, tile_h, tile_imgs, tiles_per_img, m_tiles;
-    int a_c, c_chunks, n_taps, n_total;
+    int a_c, c_chunks, n_taps, n_total, n_phases;
     int8_t tap_map[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
     int8_t tap_dh[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
     int8_t tap_dw[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
@@ -53,15 +54,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                const __grid_constant__ CUtensorMap mapB, const TgParams p)
 {
     constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-    constexpr int CH = BLOCK_N >= 32 ? 32 : 16;          // columns per tcgen05.ld
+    constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;     // TMEM columns of one accumulator
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                     // double-buffered: epilogue(i) overlaps mainloop(i+1)
+    constexpr int CH = BLOCK_N >= 32 ? 32 : 16;                      // columns per tcgen05.ld
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-byte alignment
@@ -69,22 +71,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
     const uint32_t bar_full = sB + STAGES * B_STAGE_BYTES;                // STAGES x 8 bytes
     const uint32_t bar_empty = bar_full + STAGES * 8;
-    const uint32_t bar_tmem = bar_empty + STAGES * 8;
-    const uint32_t tmem_slot = bar_tmem + 8;
+    const uint32_t bar_acc_full = bar_empty + STAGES * 8;                 // 2 x 8
+    const uint32_t bar_acc_empty = bar_acc_full + 16;                     // 2 x 8
+    const uint32_t tmem_slot = bar_acc_empty + 16;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, n_blk = blockIdx.y, phase = blockIdx.z;
     const int num_kb = p.n_taps * p.c_chunks;
-
-    // tile origin in the virtual output grid
-    int img0, h0;
-    if (p.tile_imgs == 1) { img0 = m_tile / p.tiles_per_img; h0 = (m_tile - img0 * p.tiles_per_img) * p.tile_h; }
-    else { img0 = m_tile * p.tile_imgs; h0 = 0; }
+    const int n_blks = p.n_total / BLOCK_N;
+    const int tiles_per_phase = p.m_tiles * n_blks;
+    const int total_tiles = tiles_per_phase * p.n_phases;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_tmem, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, 4); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -94,21 +94,30 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    // persistent: CTA c processes tiles c, c + grid, c + 2 grid, ...   tile -> (phase, m_tile, n_blk), n_blk fastest
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t par = (uint32_t)((kb / STAGES) & 1);
-                mbar_wait(bar_empty + 8 * s, par ^ 1u);
-                mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-                const int tap = kb / p.c_chunks, cc = kb - tap * p.c_chunks;
-                const int mi = p.tap_map[phase][tap];
-                const CUtensorMap *ma = mi == 0 ? &mapA0 : (mi == 1 ? &mapA1 : (mi == 2 ? &mapA2 : &mapA3));
-                tma_load_4d(sA + s * A_STAGE_BYTES, ma, bar_full + 8 * s, cc * BLOCK_K, (int)p.tap_dw[phase][tap],
-                            h0 + (int)p.tap_dh[phase][tap], img0);
-                tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, bar_full + 8 * s, tap * p.a_c + cc * BLOCK_K,
-                            phase * p.n_total + n_blk * BLOCK_N);
+            uint32_t g = 0;                                            // running k-block counter across tiles
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int phase = tile / tiles_per_phase, rem = tile - phase * tiles_per_phase;
+                const int m_tile = rem / n_blks, n_blk = rem - m_tile * n_blks;
+                int img0, h0;
+                if (p.tile_imgs == 1) { img0 = m_tile / p.tiles_per_img; h0 = (m_tile - img0 * p.tiles_per_img) * p.tile_h; }
+                else { img0 = m_tile * p.tile_imgs; h0 = 0; }
+                for (int kb = 0; kb < num_kb; kb++, g++) {
+                    const int s = g % STAGES;
+                    const uint32_t par = (g / STAGES) & 1u;
+                    mbar_wait(bar_empty + 8 * s, par ^ 1u);
+                    mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+                    const int tap = kb / p.c_chunks, cc = kb - tap * p.c_chunks;
+                    const int mi = p.tap_map[phase][tap];
+                    const CUtensorMap *ma = mi == 0 ? &mapA0 : (mi == 1 ? &mapA1 : (mi == 2 ? &mapA2 : &mapA3));
+                    tma_load_4d(sA + s * A_STAGE_BYTES, ma, bar_full + 8 * s, cc * BLOCK_K, (int)p.tap_dw[phase][tap],
+                                h0 + (int)p.tap_dh[phase][tap], img0);
+                    tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, bar_full + 8 * s, tap * p.a_c + cc * BLOCK_K,
+                                phase * p.n_total + n_blk * BLOCK_N);
+                }
             }
         }
         __syncwarp();
@@ -116,21 +125,28 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t par = (uint32_t)((kb / STAGES) & 1);
-                mbar_wait(bar_full + 8 * s, par);
+            uint32_t g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+                const uint32_t buf = it & 1u;
+                mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
                 tc_fence_after();
-                const uint64_t da = umma_desc_sw128(sA + s * A_STAGE_BYTES, 0, 1024);
-                const uint64_t db = umma_desc_sw128(sB + s * B_STAGE_BYTES, 0, 1024);
+                const uint32_t acc = tmem_base + buf * ACC_COLS;
+                for (int kb = 0; kb < num_kb; kb++, g++) {
+                    const int s = g % STAGES;
+                    const uint32_t par = (g / STAGES) & 1u;
+                    mbar_wait(bar_full + 8 * s, par);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(sA + s * A_STAGE_BYTES, 0, 1024);
+                    const uint64_t db = umma_desc_sw128(sB + s * B_STAGE_BYTES, 0, 1024);
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-                    // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
-                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                        // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
+                        umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(bar_empty + 8 * s);           // smem stage reusable once these MMAs retire
                 }
-                umma_commit(bar_empty + 8 * s);           // smem stage reusable once these MMAs retire
+                umma_commit(bar_acc_full + 8 * buf);          // accumulator complete
             }
-            umma_commit(bar_tmem);                        // accumulator complete
         }
         __syncwarp();
     } else {
@@ -138,114 +154,127 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;                    // row of the 128-row tile
         const int per_img = p.tile_h * p.q_w;
-        const int i_img = row / per_img, rem = row - i_img * per_img;
-        const int i_row = rem / p.q_w, i_col = rem - i_row * p.q_w;
-        const int img = img0 + i_img;
-        const bool valid = img < p.a_n;
-        const int oh = (h0 + i_row) * p.out_sh + p.out_oh[phase];
-        const int ow = i_col * p.out_sw + p.out_ow[phase];
-        const size_t pix = ((size_t)img * p.out_h + oh) * p.out_w + ow;
+        const int i_img = row / per_img, rem_r = row - i_img * per_img;
+        const int i_row = rem_r / p.q_w, i_col = rem_r - i_row * p.q_w;
         const float inv_sigma = p.sigma ? 1.0f / __ldg(p.sigma) : 1.0f;
-
-        mbar_wait(bar_tmem, 0);
-        tc_fence_after();
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+            const int phase = tile / tiles_per_phase, rem = tile - phase * tiles_per_phase;
+            const int m_tile = rem / n_blks, n_blk = rem - m_tile * n_blks;
+            int img0, h0;
+            if (p.tile_imgs == 1) { img0 = m_tile / p.tiles_per_img; h0 = (m_tile - img0 * p.tiles_per_img) * p.tile_h; }
+            else { img0 = m_tile * p.tile_imgs; h0 = 0; }
+            const int img = img0 + i_img;
+            const bool valid = img < p.a_n;
+            const int oh = (h0 + i_row) * p.out_sh + p.out_oh[phase];
+            const int ow = i_col * p.out_sw + p.out_ow[phase];
+            const size_t pix = ((size_t)img * p.out_h + oh) * p.out_w + ow;
+            const uint32_t buf = it & 1u;
+            mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1u);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
-            uint32_t raw[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            if constexpr (CH == 32) tmem_ld_32x32(taddr, raw);
-            else tmem_ld_32x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&raw));
-            tmem_ld_wait();
-            const int n0 = n_blk * BLOCK_N + c0;
-            float v[CH];
-#pragma unroll
-            for (int j = 0; j < CH; j++) v[j] = __uint_as_float(raw[j]) * inv_sigma;
-
-            if (p.epi_mode == IPR_EPI_BIAS_LRELU) {
-#pragma unroll
-                for (int j = 0; j < CH; j++) {
-                    float t = v[j] + (p.bias ? __ldg(p.bias + n0 + j) : 0.0f);
-                    v[j] = t > 0.0f ? t : t * p.slope;
+            for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+                uint32_t raw[32];
+                const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                if constexpr (CH == 32) tmem_ld_32x32(taddr, raw);
+                else tmem_ld_32x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&raw));
+                tmem_ld_wait();
+                if (c0 + CH >= BLOCK_N) {
+                    // last chunk is in registers: hand the accumulator back to the MMA warp before the slow part
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
                 }
-            } else if (p.epi_mode == IPR_EPI_MASK) {
-                if (valid) {
-                    const uint4 *mp = reinterpret_cast<const uint4 *>(p.mask + pix * p.out_c + n0);
+                const int n0 = n_blk * BLOCK_N + c0;
+                float v[CH];
 #pragma unroll
-                    for (int g = 0; g < CH / 8; g++) {
-                        const uint4 mv = __ldg(mp + g);
-                        const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+                for (int j = 0; j < CH; j++) v[j] = __uint_as_float(raw[j]) * inv_sigma;
+
+                if (p.epi_mode == IPR_EPI_BIAS_LRELU) {
 #pragma unroll
-                        for (int h = 0; h < 4; h++) {
-                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[h]);
-                            const float2 f2 = __bfloat1622float2(b2);
-                            v[g * 8 + 2 * h] *= f2.x > 0.0f ? 1.0f : p.slope;
-                            v[g * 8 + 2 * h + 1] *= f2.y > 0.0f ? 1.0f : p.slope;
+                    for (int j = 0; j < CH; j++) {
+                        float t = v[j] + (p.bias ? __ldg(p.bias + n0 + j) : 0.0f);
+                        v[j] = t > 0.0f ? t : t * p.slope;
+                    }
+                } else if (p.epi_mode == IPR_EPI_MASK) {
+                    if (valid) {
+                        const uint4 *mp = reinterpret_cast<const uint4 *>(p.mask + pix * p.out_c + n0);
+#pragma unroll
+                        for (int gq = 0; gq < CH / 8; gq++) {
+                            const uint4 mv = __ldg(mp + gq);
+                            const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                            for (int h = 0; h < 4; h++) {
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[h]);
+                                const float2 f2 = __bfloat1622float2(b2);
+                                v[gq * 8 + 2 * h] *= f2.x > 0.0f ? 1.0f : p.slope;
+                                v[gq * 8 + 2 * h + 1] *= f2.y > 0.0f ? 1.0f : p.slope;
+                            }
                         }
                     }
+                } else if (p.epi_mode == IPR_EPI_TANH_NCHW) {
+#pragma unroll
+                    for (int j = 0; j < CH; j++) v[j] = tanhf(v[j]);
                 }
-            } else if (p.epi_mode == IPR_EPI_TANH_NCHW) {
-#pragma unroll
-                for (int j = 0; j < CH; j++) v[j] = tanhf(v[j]);
-            }
 
-            if (p.stats) {
-                // per-column sum / sum of squares over this warp's 32 rows: 31-step transposing butterfly
-                float s1[CH], s2[CH];
+                if (p.stats) {
+                    // per-column sum / sum of squares over this warp's 32 rows: 31-step transposing butterfly
+                    float s1[CH], s2[CH];
 #pragma unroll
-                for (int j = 0; j < CH; j++) { const float t = valid ? v[j] : 0.0f; s1[j] = t; s2[j] = t * t; }
+                    for (int j = 0; j < CH; j++) { const float t = valid ? v[j] : 0.0f; s1[j] = t; s2[j] = t * t; }
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
-                    if (off < CH) {
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+                        if (off < CH) {
 #pragma unroll
-                        for (int i = 0; i < off; i++) {
-                            const float snd1 = up ? s1[i] : s1[i + off], kp1 = up ? s1[i + off] : s1[i];
-                            const float snd2 = up ? s2[i] : s2[i + off], kp2 = up ? s2[i + off] : s2[i];
-                            s1[i] = kp1 + __shfl_xor_sync(0xffffffffu, snd1, off);
-                            s2[i] = kp2 + __shfl_xor_sync(0xffffffffu, snd2, off);
-                        }
-                    } else {   // CH == 16 and off == 16: plain pairwise sum, both halves keep all 16 columns
+                            for (int i = 0; i < off; i++) {
+                                const float snd1 = up ? s1[i] : s1[i + off], kp1 = up ? s1[i + off] : s1[i];
+                                const float snd2 = up ? s2[i] : s2[i + off], kp2 = up ? s2[i + off] : s2[i];
+                                s1[i] = kp1 + __shfl_xor_sync(0xffffffffu, snd1, off);
+                                s2[i] = kp2 + __shfl_xor_sync(0xffffffffu, snd2, off);
+                            }
+                        } else {   // CH == 16 and off == 16: plain pairwise sum, both halves keep all 16 columns
 #pragma unroll
-                        for (int i = 0; i < CH; i++) {
-                            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
-                            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+                            for (int i = 0; i < CH; i++) {
+                                s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+                                s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+                            }
                         }
                     }
-                }
-                // lane L now holds column (L mod CH)
-                if (lane < CH) {
-                    const size_t srow = ((size_t)phase * p.m_tiles + m_tile) * 4 + q;
-                    float *dst = p.stats + srow * 2 * p.n_total;
-                    dst[n0 + lane] = s1[0];
-                    dst[p.n_total + n0 + lane] = s2[0];
-                }
-            }
-
-            if (!valid) continue;
-            if (p.epi_mode == IPR_EPI_TANH_NCHW || p.epi_mode == IPR_EPI_LINEAR_NCHW) {
-                float *o = reinterpret_cast<float *>(p.out);
-#pragma unroll
-                for (int j = 0; j < CH; j++) {
-                    const int n = n0 + j;
-                    if (n < p.n_valid) o[(((size_t)img * p.out_c + n) * p.out_h + oh) * p.out_w + ow] = v[j];
-                }
-            } else if (p.epi_mode == IPR_EPI_LINEAR_F32) {
-                float *o = reinterpret_cast<float *>(p.out) + pix * p.out_c + n0;
-#pragma unroll
-                for (int j = 0; j < CH; j++) if (n0 + j < p.n_valid) o[j] = v[j];
-            } else {
-                __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_c + n0;
-                if (n0 + CH <= p.n_valid) {
-#pragma unroll
-                    for (int g = 0; g < CH / 8; g++) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); pk.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-                        pk.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); pk.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-                        reinterpret_cast<uint4 *>(o)[g] = pk;
+                    if (lane < CH) {                      // lane L now holds column (L mod CH)
+                        const size_t srow = ((size_t)phase * p.m_tiles + m_tile) * 4 + q;
+                        float *dst = p.stats + srow * 2 * p.n_total;
+                        dst[n0 + lane] = s1[0];
+                        dst[p.n_total + n0 + lane] = s2[0];
                     }
+                }
+
+                if (!valid) continue;
+                if (p.epi_mode == IPR_EPI_TANH_NCHW || p.epi_mode == IPR_EPI_LINEAR_NCHW) {
+                    float *o = reinterpret_cast<float *>(p.out);
+#pragma unroll
+                    for (int j = 0; j < CH; j++) {
+                        const int n = n0 + j;
+                        if (n < p.n_valid) o[(((size_t)img * p.out_c + n) * p.out_h + oh) * p.out_w + ow] = v[j];
+                    }
+                } else if (p.epi_mode == IPR_EPI_LINEAR_F32) {
+                    float *o = reinterpret_cast<float *>(p.out) + pix * p.out_c + n0;
+#pragma unroll
+                    for (int j = 0; j < CH; j++) if (n0 + j < p.n_valid) o[j] = v[j];
                 } else {
+                    __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_c + n0;
+                    if (n0 + CH <= p.n_valid) {
 #pragma unroll
-                    for (int j = 0; j < CH; j++) if (n0 + j < p.n_valid) o[j] = __float2bfloat16(v[j]);
+                        for (int gq = 0; gq < CH / 8; gq++) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(v[gq * 8 + 0], v[gq * 8 + 1]); pk.y = pack_bf16x2(v[gq * 8 + 2], v[gq * 8 + 3]);
+                            pk.z = pack_bf16x2(v[gq * 8 + 4], v[gq * 8 + 5]); pk.w = pack_bf16x2(v[gq * 8 + 6], v[gq * 8 + 7]);
+                            reinterpret_cast<uint4 *>(o)[gq] = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CH; j++) if (n0 + j < p.n_valid) o[j] = __float2bfloat16(v[j]);
+                    }
                 }
             }
         }
@@ -258,7 +287,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 template <int BLOCK_N, int STAGES>
 int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3 grid, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 2) * 8 + 1024 + 64;
+    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 4) * 8 + 1024 + 64;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -266,7 +295,9 @@ int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    tapgemm_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], mb, p);
+    const int total = (int)(grid.x * grid.y * grid.z);
+    const int ctas = total < ipr_sm_count() ? total : ipr_sm_count();       // persistent: one CTA per SM
+    tapgemm_kernel<BLOCK_N, STAGES><<<ctas, NUM_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], mb, p);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -310,7 +341,8 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     IPR_REQUIRE(d->a_c % BLOCK_K == 0, IPR_E_UNSUPPORTED);
     IPR_REQUIRE(d->n_taps >= 1 && d->n_taps <= IPR_TG_MAX_TAPS && d->n_phases >= 1 && d->n_phases <= IPR_TG_MAX_PHASES,
                 IPR_E_SHAPE);
-    IPR_REQUIRE(d->block_n == 16 || d->block_n == 32 || d->block_n == 64 || d->block_n == 128, IPR_E_UNSUPPORTED);
+    IPR_REQUIRE(d->block_n == 16 || d->block_n == 32 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256,
+                IPR_E_UNSUPPORTED);
     IPR_REQUIRE(d->n_total > 0 && d->n_total % d->block_n == 0, IPR_E_SHAPE);
     IPR_REQUIRE(ipr_aligned16(d->a) && ipr_aligned16(d->b) && ipr_aligned16(d->out), IPR_E_ALIGN);
     IPR_REQUIRE(d->epi_mode >= 0 && d->epi_mode <= 5, IPR_E_SHAPE);
@@ -324,6 +356,7 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     if (rc != IPR_OK) return rc;
     p.a_n = d->a_n; p.q_h = d->q_h; p.q_w = d->q_w;
     p.a_c = d->a_c; p.c_chunks = d->a_c / BLOCK_K; p.n_taps = d->n_taps; p.n_total = d->n_total;
+    p.n_phases = d->n_phases;
     for (int ph = 0; ph < IPR_TG_MAX_PHASES; ph++) {
         for (int t = 0; t < IPR_TG_MAX_TAPS; t++) {
             p.tap_map[ph][t] = d->tap_map[ph][t]; p.tap_dh[ph][t] = d->tap_dh[ph][t]; p.tap_dw[ph][t] = d->tap_dw[ph][t];
@@ -370,9 +403,10 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     dim3 grid((unsigned)p.m_tiles, (unsigned)(d->n_total / d->block_n), (unsigned)d->n_phases);
     cudaStream_t st = ipr_cu(stream);
     switch (d->block_n) {
-        case 16:  return launch<16, 4>(ma, mb, p, grid, st);
-        case 32:  return launch<32, 4>(ma, mb, p, grid, st);
-        case 64:  return launch<64, 4>(ma, mb, p, grid, st);
-        default:  return launch<128, 3>(ma, mb, p, grid, st);
+        case 16:  return launch<16, 8>(ma, mb, p, grid, st);
+        case 32:  return launch<32, 8>(ma, mb, p, grid, st);
+        case 64:  return launch<64, 8>(ma, mb, p, grid, st);
+        case 128: return launch<128, 6>(ma, mb, p, grid, st);
+        default:  return launch<256, 4>(ma, mb, p, grid, st);
     }
 }

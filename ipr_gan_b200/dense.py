@@ -73,7 +73,7 @@ _T2 = {0: ((1, 0), (3, -1)), 1: ((0, 1), (2, 0))}             # r -> ((kh, d), (
 
 
 def pick_block_n(n):
-    for bn in (128, 64, 32, 16):
+    for bn in (256, 128, 64, 32, 16):
         if n % bn == 0:
             return bn
     raise ValueError("N must be a multiple of 16, got %d" % n)
