@@ -228,12 +228,14 @@ size_t ipr_wgrad_workspace_bytes(const ipr_wgrad_t *d_host);
 int    ipr_wgrad_total_kblocks(const ipr_wgrad_t *d_host);     /* 64-pixel blocks of the reduction */
 int    ipr_wgrad_bf16(const ipr_wgrad_t *d_host, ipr_stream_t stream);
 
-/* For every output row n:  grad[row(n)*s_n + out_pos[j]] (+)= scale * sum_splits ws[split][src_idx[j] / k_total][n][src_idx[j] % k_total]
- * for j < n_out, out_pos ascending (row(n) = row_map ? row_map[n] : n).  Adds the splits in a fixed order and permutes
- * the GEMM layout into the parameter's own layout ((O,I,kh,kw), (I,O,kh,kw) or (O,I)) with coalesced reads and writes. */
+/* number of CTA tiles per split (the caller picks `splits` so that tiles*splits ~ number of SMs) */
+int ipr_wgrad_tiles(const ipr_wgrad_t *d_host);
+
+/* grad[row(n)*s_n + dst_off[p*k_total + k]] (+)= scale * sum_splits ws[split][p][n][k]   (dst_off < 0: skipped;
+ * row(n) = row_map ? row_map[n] : n).  Adds the splits in a fixed order and scatters from the GEMM layout into the
+ * parameter's own layout ((O,I,kh,kw), (I,O,kh,kw) or (O,I)). */
 int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_rows, int k_total,
-                         const int32_t *src_idx, const int32_t *out_pos, int n_out,
-                         const int32_t *row_map, int64_t s_n, float *grad,
+                         const int32_t *dst_off, const int32_t *row_map, int64_t s_n, float *grad,
                          int accumulate, float scale, ipr_stream_t stream);
 
 /* ------------------------------------------------------------------ memory-bound layers around the GEMMs */

@@ -170,7 +170,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int ow = i_col * p.out_sw + p.out_ow[phase];
             const size_t pix = ((size_t)img * p.out_h + oh) * p.out_w + ow;
             const uint32_t buf = it & 1u;
-            mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1u);
+            mbar_wait_backoff(bar_acc_full + 8 * buf, (it >> 1) & 1u);
             tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {

@@ -37,6 +37,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// Long waits (epilogue warps waiting for a whole main loop): back off between probes so that 128 spinning threads do
+// not compete with the single TMA-producer / MMA-issuer threads for issue slots and the mbarrier unit.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
+
 // ------------------------------------------------------------------------------------ device: TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -14,6 +14,7 @@
 // in a fixed order (deterministic) and scatters into the parameter's own (reference) layout.
 #include "ipr_common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -21,8 +22,8 @@ using namespace tc;
 
 constexpr int KB_PIX = 64;                    // pixels per k-block
 constexpr int UNIT_BYTES = KB_PIX * 128;      // one 64-channel x 64-pixel box
-constexpr int STAGE_BYTES = 4 * UNIT_BYTES;   // 2 Y blocks + 2 X units
-constexpr int STAGES = 3;
+// Tile configuration (template): X_UNITS (tap, 64-channel) units of X per CTA tile -> N = 64*X_UNITS; STAGES smem stages of
+// (2 + X_UNITS) * 8 KB.
 constexpr int NUM_THREADS = 192;
 constexpr int UMMA_K = 16;
 
@@ -39,26 +40,28 @@ struct WgParams {
 
 struct Maps { CUtensorMap y[4]; CUtensorMap x[4]; };
 
+template <int X_UNITS, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS)
 wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
 {
+    constexpr int STAGE_BYTES = (2 + X_UNITS) * UNIT_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_full = smem_base + STAGES * STAGE_BYTES;
     const uint32_t bar_empty = bar_full + STAGES * 8;
     const uint32_t bar_tmem = bar_empty + STAGES * 8;
     const uint32_t tmem_slot = bar_tmem + 8;
-    constexpr uint32_t TMEM_COLS = 128;
+    constexpr uint32_t TMEM_COLS = 64 * X_UNITS < 32 ? 32 : 64 * X_UNITS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = (p.n_units + 1) >> 1;
+    const int n_tiles = (p.n_units + X_UNITS - 1) / X_UNITS;
     const int m_blk = blockIdx.x / n_tiles, n_tile = blockIdx.x - m_blk * n_tiles;
     const int split = blockIdx.y, phase = blockIdx.z;
     const int kb0 = split * p.kb_per_split;
     const int kb1 = min(p.total_kb, kb0 + p.kb_per_split);
     const int num_kb = max(0, kb1 - kb0);
-    const int unit0 = 2 * n_tile;
-    const bool has_u1 = unit0 + 1 < p.n_units;
+    const int unit0 = X_UNITS * n_tile;
+    const int units_here = min(X_UNITS, p.n_units - unit0);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -83,13 +86,11 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
                 if (p.kb_imgs == 1) { img0 = kb / p.kb_per_img; h0 = (kb - img0 * p.kb_per_img) * p.kb_rows; }
                 else { img0 = kb * p.kb_imgs; h0 = 0; }
                 mbar_wait(bar_empty + 8 * s, par ^ 1u);
-                mbar_expect_tx(bar_full + 8 * s, has_u1 ? STAGE_BYTES : STAGE_BYTES - UNIT_BYTES);
+                mbar_expect_tx(bar_full + 8 * s, (2 + units_here) * UNIT_BYTES);
                 const uint32_t st = smem_base + s * STAGE_BYTES;
                 tma_load_4d(st, my, bar_full + 8 * s, (2 * m_blk) * 64, 0, h0, img0);
                 tma_load_4d(st + UNIT_BYTES, my, bar_full + 8 * s, (2 * m_blk + 1) * 64, 0, h0, img0);
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    if (u == 1 && !has_u1) break;
+                for (int u = 0; u < units_here; u++) {
                     const int unit = unit0 + u;
                     const int tap = unit / p.x_chunks, cc = unit - tap * p.x_chunks;
                     const CUtensorMap *mx = &maps.x[p.tap_map[phase][tap]];
@@ -101,7 +102,7 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, 128, /*a_major=MN*/ 1, /*b_major=MN*/ 1);
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 64 * X_UNITS, /*a_major=MN*/ 1, /*b_major=MN*/ 1);
             for (int i = 0; i < num_kb; i++) {
                 const int s = i % STAGES;
                 const uint32_t par = (uint32_t)((i / STAGES) & 1);
@@ -124,9 +125,9 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
         const int q = warp & 3;
         const int n = m_blk * 128 + q * 32 + lane;        // output channel (row of dW)
         float *dst_row = p.ws + (((size_t)split * p.n_phases + phase) * p.n_pad + n) * p.k_total;
-        if (num_kb > 0) { mbar_wait(bar_tmem, 0); tc_fence_after(); }
+        if (num_kb > 0) { mbar_wait_backoff(bar_tmem, 0); tc_fence_after(); }
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = 0; c0 < 64 * X_UNITS; c0 += 32) {
             const int unit = unit0 + (c0 >> 6);
             if (unit >= p.n_units) break;
             uint32_t raw[32];
@@ -149,32 +150,68 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// One CTA per output row n: sum the splits of ws[.][p][n][k] into shared memory (coalesced reads, fixed order),
-// then write grad[row(n)*s_n + out_pos[j]] (+)= scale * smem[src_idx[j]] for j in ascending address order
-// (coalesced writes): the GEMM layout [tap][c] is permuted into the parameter's own layout on the way out.
+// grad[row(n)*s_n + dst_off[p*k_total + k]] (+)= scale * sum_splits ws[split][p][n][k]   (dst_off < 0: padding column)
+// One thread per (p, n, k): coalesced reads along k, 8 independent loads in flight over the splits (fixed summation
+// order), scattered 4-byte writes into the parameter's own layout (the output is tiny compared with the partials).
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int phases, int n_pad, int k_total,
-                    const int *__restrict__ src_idx, const int *__restrict__ out_pos, int n_out,
-                    const int *__restrict__ row_map, long long s_n, float *__restrict__ grad, int accumulate, float scale)
+wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int phases, int n_rows, int n_pad, int k_total,
+                    const int *__restrict__ dst_off, const int *__restrict__ row_map, long long s_n,
+                    float *__restrict__ grad, int accumulate, float scale)
 {
-    extern __shared__ float sm[];
-    const int n = blockIdx.x;
+    const long long total = (long long)phases * n_rows * k_total;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int k = (int)(e % k_total);
+    const long long t = e / k_total;
+    const int n = (int)(t % n_rows);
+    const int ph = (int)(t / n_rows);
+    const int off = __ldg(dst_off + (size_t)ph * k_total + k);
+    if (off < 0) return;
     const size_t split_stride = (size_t)phases * n_pad * k_total;
-    for (int e = threadIdx.x; e < phases * k_total; e += blockDim.x) {
-        const int ph = e / k_total, k = e - ph * k_total;
-        const float *src = ws + ((size_t)ph * n_pad + n) * k_total + k;
-        float acc = 0.0f;
-        for (int s = 0; s < splits; s++) acc += src[s * split_stride];
-        sm[e] = acc * scale;
+    const float *src = ws + ((size_t)ph * n_pad + n) * k_total + k;
+    float acc = 0.0f;
+    int s = 0;
+    for (; s + 8 <= splits; s += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = src[(size_t)(s + j) * split_stride];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += v[j];
     }
-    __syncthreads();
+    for (; s < splits; s++) acc += src[(size_t)s * split_stride];
     const int rn = row_map ? __ldg(row_map + n) : n;
-    float *dst = grad + (size_t)rn * s_n;
-    for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
-        const float v = sm[__ldg(src_idx + j)];
-        const int o = __ldg(out_pos + j);
-        dst[o] = accumulate ? dst[o] + v : v;
+    float *dst = grad + (size_t)rn * s_n + off;
+    *dst = accumulate ? *dst + acc * scale : acc * scale;
+}
+
+// tile configuration: IPR_WGRAD_CFG = 0: N=128, 3 stages (2 CTAs/SM) | 1: N=128, 6 stages | 2: N=256, 4 stages | 3: N=64, 8 stages.
+// Measured on B200 (scripts/wg_sweep.sh): the MN-major tcgen05.mma stream, not the operand loads, paces this kernel
+// (skipping the TMA loads entirely only drops c3 from 45 to 37 us), and two co-resident CTAs interleave their MMA
+// streams better than one deep pipeline, so config 0 with ~2 CTAs per SM is the default.
+int wgrad_config() {
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char *e = getenv("IPR_WGRAD_CFG");
+        cfg = e ? atoi(e) : 0;
+        if (cfg < 0 || cfg > 3) cfg = 0;
     }
+    return cfg;
+}
+int wgrad_x_units() { const int c = wgrad_config(); return c == 2 ? 4 : (c == 3 ? 1 : 2); }
+
+template <int X_UNITS, int STAGES>
+int launch_wgrad(const Maps &maps, const WgParams &p, dim3 grid, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)STAGES * (2 + X_UNITS) * UNIT_BYTES + (2 * STAGES + 2) * 8 + 1024 + 64;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<X_UNITS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    wgrad_kernel<X_UNITS, STAGES><<<grid, NUM_THREADS, smem, st>>>(maps, p);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
 }
 
 int geometry(const ipr_wgrad_t *d, WgParams &p)
@@ -271,39 +308,36 @@ extern "C" int ipr_wgrad_bf16(const ipr_wgrad_t *d, ipr_stream_t stream)
     rc = make_maps(d->x, d->x_c, xh, xw, d->n_imgs, d->x_parity, box, maps.x);
     if (rc) return rc;
 
-    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8 + 1024 + 64;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
-    const int n_tiles = (p.n_units + 1) / 2;
+    const int xu = wgrad_x_units();
+    const int n_tiles = (p.n_units + xu - 1) / xu;
     dim3 grid((unsigned)((p.n_pad / 128) * n_tiles), (unsigned)d->splits, (unsigned)d->n_phases);
-    wgrad_kernel<<<grid, NUM_THREADS, smem, ipr_cu(stream)>>>(maps, p);
-    IPR_LAUNCH_CHECK();
-    return IPR_OK;
+    switch (wgrad_config()) {
+        case 0:  return launch_wgrad<2, 3>(maps, p, grid, ipr_cu(stream));
+        case 1:  return launch_wgrad<2, 6>(maps, p, grid, ipr_cu(stream));
+        case 2:  return launch_wgrad<4, 4>(maps, p, grid, ipr_cu(stream));
+        default: return launch_wgrad<1, 8>(maps, p, grid, ipr_cu(stream));
+    }
+}
+
+extern "C" int ipr_wgrad_tiles(const ipr_wgrad_t *d)
+{
+    if (!d) return IPR_E_NULL;
+    const int n_units = d->n_taps * (d->x_c / 64);
+    const int xu = wgrad_x_units();
+    return ((d->y_c + 127) / 128) * ((n_units + xu - 1) / xu) * d->n_phases;
 }
 
 extern "C" int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_rows, int k_total,
-                                    const int32_t *src_idx, const int32_t *out_pos, int n_out,
-                                    const int32_t *row_map, int64_t s_n, float *grad,
+                                    const int32_t *dst_off, const int32_t *row_map, int64_t s_n, float *grad,
                                     int accumulate, float scale, ipr_stream_t stream)
 {
-    IPR_REQUIRE(workspace && src_idx && out_pos && grad, IPR_E_NULL);
-    IPR_REQUIRE(splits > 0 && phases > 0 && n_rows > 0 && k_total > 0 && n_out > 0, IPR_E_SHAPE);
+    IPR_REQUIRE(workspace && dst_off && grad, IPR_E_NULL);
+    IPR_REQUIRE(splits > 0 && phases > 0 && n_rows > 0 && k_total > 0, IPR_E_SHAPE);
     const int n_pad = ((n_rows + 127) / 128) * 128;
-    const size_t smem = (size_t)phases * k_total * sizeof(float);
-    IPR_REQUIRE(smem <= 160 * 1024, IPR_E_UNSUPPORTED);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
-    wgrad_reduce_kernel<<<(unsigned)n_rows, 256, smem, ipr_cu(stream)>>>(workspace, splits, phases, n_pad, k_total, src_idx,
-                                                                       out_pos, n_out, row_map, (long long)s_n, grad,
-                                                                       accumulate, scale);
+    const long long total = (long long)phases * n_rows * k_total;
+    wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ipr_cu(stream)>>>(workspace, splits, phases, n_rows, n_pad,
+                                                                                   k_total, dst_off, row_map,
+                                                                                   (long long)s_n, grad, accumulate, scale);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

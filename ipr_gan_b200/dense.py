@@ -214,6 +214,7 @@ class WGrad(ctypes.Structure):
 
 
 _SM_COUNT = 148
+_WGRAD_OVERSUB = int(__import__('os').environ.get('IPR_WGRAD_OVERSUB', '2'))
 
 
 class WGradPlan(object):
@@ -249,18 +250,14 @@ class WGradPlan(object):
                             col_off[ph, t * self.x_c:(t + 1) * self.x_c] = c * (ksz * ksz) + kh * ksz + kw
                 s_n = ksz * ksz if k == "convT4s2" else weight_shape[1] * ksz * ksz
         self.s_n = int(s_n)
-        flat_off = col_off.reshape(-1).to(torch.int64)
-        src = torch.nonzero(flat_off >= 0).reshape(-1)
-        order = torch.argsort(flat_off[src], stable=True)
-        self.src_idx_host = src[order].to(torch.int32).contiguous()          # phase * k_total + k
-        self.out_pos_host = flat_off[src][order].to(torch.int32).contiguous()   # ascending offsets inside a row
+        self.dst_off_host = col_off.reshape(-1).to(torch.int32).contiguous()   # [phase * k_total + k] -> offset in a row
         self._dev = {}
 
     def _tables(self, device):
         key = str(device)
         if key not in self._dev:
             rp = self.row_perm.to(device=device, dtype=torch.int32).contiguous() if self.row_perm is not None else None
-            self._dev[key] = (self.src_idx_host.to(device), self.out_pos_host.to(device), rp)
+            self._dev[key] = (self.dst_off_host.to(device), rp)
         return self._dev[key]
 
     def run(self, y, x, grad, accumulate=False, scale=1.0, splits=None):
@@ -269,6 +266,7 @@ class WGradPlan(object):
             L.ipr_wgrad_bf16.argtypes = [ctypes.POINTER(WGrad), ctypes.c_void_p]
             L.ipr_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(WGrad)]
             L.ipr_wgrad_total_kblocks.argtypes = [ctypes.POINTER(WGrad)]
+            L.ipr_wgrad_tiles.argtypes = [ctypes.POINTER(WGrad)]
             L._wg_bound = True
         assert y.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and y.is_contiguous() and x.is_contiguous()
         assert grad.dtype == torch.float32 and grad.is_contiguous()
@@ -288,9 +286,9 @@ class WGradPlan(object):
         if kblocks < 0:
             check(kblocks, "ipr_wgrad_total_kblocks")
         if splits is None:
-            n_units = self.n_taps * (xc // 64)
-            ctas = ((self.rows + 127) // 128) * ((n_units + 1) // 2) * self.n_phases
-            splits = max(1, min(kblocks // 4 if kblocks >= 8 else 1, (3 * _SM_COUNT + ctas - 1) // ctas, 64))
+            tiles = L.ipr_wgrad_tiles(ctypes.byref(d))           # one CTA per SM (48 KB stages): fill the chip once
+            target = _SM_COUNT * _WGRAD_OVERSUB
+            splits = max(1, min(kblocks // 4 if kblocks >= 8 else 1, (target + tiles - 1) // tiles, 128))
         d.splits = splits
         nbytes = L.ipr_wgrad_workspace_bytes(ctypes.byref(d))
         ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
@@ -300,9 +298,9 @@ class WGradPlan(object):
         check(L.ipr_wgrad_bf16(ctypes.byref(d), st), "ipr_wgrad_bf16(%s)" % self.fwd.kind)
         _prof_end("wgrad:" + self.fwd.kind, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps *
                   getattr(self, "k_valid_override", xc) * getattr(self, "rows_valid_override", self.rows), ev)
-        src_idx, out_pos, row_map = self._tables(x.device)
+        dst_off, row_map = self._tables(x.device)
         check(L.ipr_wgrad_reduce_f32(ws.data_ptr(), splits, self.n_phases, self.rows, self.k_total,
-                                     src_idx.data_ptr(), out_pos.data_ptr(), src_idx.numel(),
+                                     dst_off.data_ptr(),
                                      row_map.data_ptr() if row_map is not None else None,
                                      self.s_n, grad.data_ptr(), int(bool(accumulate)), float(scale), st),
               "ipr_wgrad_reduce_f32")
