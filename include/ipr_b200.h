@@ -197,10 +197,10 @@ typedef struct {
     int32_t out_sh, out_sw;
     int8_t  out_oh[IPR_TG_MAX_PHASES], out_ow[IPR_TG_MAX_PHASES];
     int32_t n_valid;               /* columns >= n_valid are not stored                              */
-    float  *stats;                 /* optional [m_tiles*n_phases*4][2][n_total] per-warp column sums / sums of squares */
+    float  *stats;                 /* optional [m_tiles*n_phases][2][n_total] per-tile column sums / sums of squares */
 } ipr_tapgemm_t;
 
-/* number of M tiles (rows of `stats` = 4 * n_phases * this) */
+/* number of M tiles (rows of `stats` = n_phases * this) */
 int ipr_tapgemm_m_tiles(const ipr_tapgemm_t *d_host);
 int ipr_tapgemm_bf16(const ipr_tapgemm_t *d_host, ipr_stream_t stream);
 
@@ -262,11 +262,13 @@ int ipr_bn_apply_relu_bf16(const void *x, void *y, const float *scale, const flo
                            int channels, ipr_stream_t stream);
 
 size_t ipr_bn_bwd_workspace_bytes(int channels);
-/* Backward of relu(batchnorm(xraw)) in training mode.  dy, xraw, act (= the forward output, used as ReLU mask),
- * dx: [rows][C] bf16.  dgamma / dbeta are written or accumulated.  If sign != NULL the white-box sign-loss
+/* Backward of relu(batchnorm(xraw)) in training mode.  dy, xraw, dx: [rows][C] bf16; scale/shift are the forward's
+ * per-channel coefficients (the ReLU mask is recomputed from xraw exactly as the forward evaluated it, so the
+ * activation tensor is not re-read).  dgamma / dbeta are written or accumulated.  If sign != NULL the white-box sign-loss
  * gradient  -sign_scale * sign_c / C  (where gamma0 - gamma_c*sign_c > 0) is added to dgamma
  * (tools/sign_model.py:48): the sign loss costs no extra pass. */
-int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const void *act, const float *gamma, const float *mean,
+int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const float *scale, const float *shift,
+                         const float *gamma, const float *mean,
                          const float *rstd, void *dx, float *dgamma, float *dbeta, int accumulate,
                          const float *sign, float gamma0, float sign_scale, void *workspace, size_t workspace_bytes,
                          int64_t rows, int channels, ipr_stream_t stream);

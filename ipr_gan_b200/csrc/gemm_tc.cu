@@ -74,6 +74,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t bar_acc_full = bar_empty + STAGES * 8;                 // 2 x 8
     const uint32_t bar_acc_empty = bar_acc_full + 16;                     // 2 x 8
     const uint32_t tmem_slot = bar_acc_empty + 16;
+    // per-warp column statistics of the current tile: [warp 4][sum | sumsq][BLOCK_N] floats (epilogue warps only)
+    float *stat_sm = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + 256);   // after the mbarriers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.n_taps * p.c_chunks;
@@ -242,10 +244,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
                     }
                     if (lane < CH) {                      // lane L now holds column (L mod CH)
-                        const size_t srow = ((size_t)phase * p.m_tiles + m_tile) * 4 + q;
-                        float *dst = p.stats + srow * 2 * p.n_total;
-                        dst[n0 + lane] = s1[0];
-                        dst[p.n_total + n0 + lane] = s2[0];
+                        stat_sm[(q * 2 + 0) * BLOCK_N + c0 + lane] = s1[0];
+                        stat_sm[(q * 2 + 1) * BLOCK_N + c0 + lane] = s2[0];
                     }
                 }
 
@@ -277,6 +277,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
             }
+            if (p.stats) {
+                // combine the four warps' column sums in a fixed order: one statistics row per tile
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int t = threadIdx.x - 64;                        // 0..127 within the epilogue warps
+                float *dst = p.stats + ((size_t)phase * p.m_tiles + m_tile) * 2 * p.n_total + n_blk * BLOCK_N;
+                for (int c = t; c < 2 * BLOCK_N; c += 128) {
+                    const int which = c / BLOCK_N, col = c - which * BLOCK_N;
+                    const float tot = stat_sm[(0 * 2 + which) * BLOCK_N + col] + stat_sm[(1 * 2 + which) * BLOCK_N + col] +
+                                      stat_sm[(2 * 2 + which) * BLOCK_N + col] + stat_sm[(3 * 2 + which) * BLOCK_N + col];
+                    dst[which * p.n_total + col] = tot;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
         }
     }
     tc_fence_before();
@@ -287,7 +300,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 template <int BLOCK_N, int STAGES>
 int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3 grid, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 4) * 8 + 1024 + 64;
+    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + 256 + 8 * BLOCK_N * 4 + 1024 + 64;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,

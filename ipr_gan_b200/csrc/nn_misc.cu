@@ -136,9 +136,9 @@ bn_apply_relu_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, const f
 // ------------------------------------------------------------------------------------ BatchNorm backward
 // pass 1: per-CTA partial sums over a slab of rows of  g = dy * (act > 0)  and  g * xhat.
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xraw, const uint4 *__restrict__ act,
-                     const float *__restrict__ mean, const float *__restrict__ rstd, long long rows, int c_vec,
-                     float *__restrict__ partial)
+bn_bwd_reduce_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xraw, const float *__restrict__ scale,
+                     const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
+                     long long rows, int c_vec, float *__restrict__ partial)
 {
     extern __shared__ float sm[];                    // [ry][2][C]
     const int C = c_vec * 8;
@@ -148,17 +148,19 @@ bn_bwd_reduce_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xra
 #pragma unroll
     for (int k = 0; k < 8; k++) sg[k] = sx[k] = 0.0f;
     if (ry < ry_n) {
-        float mu[8], rs[8];
+        float mu[8], rs[8], sc[8], sh[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { mu[k] = mean[cv * 8 + k]; rs[k] = rstd[cv * 8 + k]; }
+        for (int k = 0; k < 8; k++) {
+            mu[k] = mean[cv * 8 + k]; rs[k] = rstd[cv * 8 + k]; sc[k] = scale[cv * 8 + k]; sh[k] = shift[cv * 8 + k];
+        }
         for (long long r = (long long)blockIdx.x * ry_n + ry; r < rows; r += (long long)gridDim.x * ry_n) {
-            float d[8], xv[8], av[8];
+            float d[8], xv[8];
             unpack8(__ldg(dy + r * c_vec + cv), d);
             unpack8(__ldg(xraw + r * c_vec + cv), xv);
-            unpack8(__ldg(act + r * c_vec + cv), av);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const float g = av[k] > 0.0f ? d[k] : 0.0f;
+                // ReLU mask recomputed exactly as the forward computed its input (same fmaf): no activation re-read
+                const float g = fmaf(xv[k], sc[k], sh[k]) > 0.0f ? d[k] : 0.0f;
                 sg[k] += g;
                 sx[k] += g * (xv[k] - mu[k]) * rs[k];
             }
@@ -211,20 +213,20 @@ bn_bwd_finalize_kernel(const float *__restrict__ partial, int rows, int C, doubl
 
 // pass 2: dx = a*g + b*xraw + d
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xraw, const uint4 *__restrict__ act,
-                    const float *__restrict__ coef, uint4 *__restrict__ dx, long long n_vec, int c_vec)
+bn_bwd_apply_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xraw, const float *__restrict__ scale,
+                    const float *__restrict__ shift, const float *__restrict__ coef, uint4 *__restrict__ dx,
+                    long long n_vec, int c_vec)
 {
     const int C = c_vec * 8;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
         const int c0 = (int)(i % c_vec) * 8;
-        float d[8], xv[8], av[8], o[8];
+        float d[8], xv[8], o[8];
         unpack8(__ldg(dy + i), d);
         unpack8(__ldg(xraw + i), xv);
-        unpack8(__ldg(act + i), av);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const float g = av[k] > 0.0f ? d[k] : 0.0f;
+            const float g = fmaf(xv[k], __ldg(scale + c0 + k), __ldg(shift + c0 + k)) > 0.0f ? d[k] : 0.0f;
             o[k] = __ldg(coef + c0 + k) * g + __ldg(coef + C + c0 + k) * xv[k] + __ldg(coef + 2 * C + c0 + k);
         }
         dx[i] = pack8(o);
@@ -346,16 +348,17 @@ extern "C" size_t ipr_bn_bwd_workspace_bytes(int channels)
     return ((size_t)ipr_sm_count() * 2 * 2 * channels + 3 * (size_t)channels) * sizeof(float);
 }
 
-extern "C" int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const void *act, const float *gamma,
+extern "C" int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const float *scale, const float *shift,
+                                    const float *gamma,
                                     const float *mean, const float *rstd, void *dx, float *dgamma, float *dbeta,
                                     int accumulate, const float *sign, float gamma0, float sign_scale,
                                     void *workspace, size_t workspace_bytes, int64_t rows, int channels,
                                     ipr_stream_t stream)
 {
-    IPR_REQUIRE(dy && xraw && act && gamma && mean && rstd && dx && dgamma && dbeta && workspace, IPR_E_NULL);
+    IPR_REQUIRE(dy && xraw && scale && shift && gamma && mean && rstd && dx && dgamma && dbeta && workspace, IPR_E_NULL);
     IPR_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0 && channels <= 2048, IPR_E_SHAPE);
     IPR_REQUIRE(workspace_bytes >= ipr_bn_bwd_workspace_bytes(channels), IPR_E_WORKSPACE);
-    IPR_REQUIRE(ipr_aligned16(dy) && ipr_aligned16(xraw) && ipr_aligned16(act) && ipr_aligned16(dx), IPR_E_ALIGN);
+    IPR_REQUIRE(ipr_aligned16(dy) && ipr_aligned16(xraw) && ipr_aligned16(dx), IPR_E_ALIGN);
     const int c_vec = channels / 8;
     IPR_REQUIRE(c_vec <= 256, IPR_E_UNSUPPORTED);
     const int ry_n = 256 / c_vec;
@@ -372,7 +375,7 @@ extern "C" int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const void
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    bn_bwd_reduce_kernel<<<(unsigned)ctas, 256, smem, st>>>((const uint4 *)dy, (const uint4 *)xraw, (const uint4 *)act,
+    bn_bwd_reduce_kernel<<<(unsigned)ctas, 256, smem, st>>>((const uint4 *)dy, (const uint4 *)xraw, scale, shift,
                                                             mean, rstd, rows, c_vec, partial);
     IPR_LAUNCH_CHECK();
     bn_bwd_finalize_kernel<<<(channels + 31) / 32, 256, 0, st>>>(partial, (int)ctas, channels, (double)rows, gamma, mean,
@@ -380,7 +383,7 @@ extern "C" int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const void
                                                                   sign_scale, coef);
     IPR_LAUNCH_CHECK();
     const long long n_vec = (long long)rows * c_vec;
-    bn_bwd_apply_kernel<<<grid_1d(n_vec, 256), 256, 0, st>>>((const uint4 *)dy, (const uint4 *)xraw, (const uint4 *)act,
+    bn_bwd_apply_kernel<<<grid_1d(n_vec, 256), 256, 0, st>>>((const uint4 *)dy, (const uint4 *)xraw, scale, shift,
                                                              coef, (uint4 *)dx, n_vec, c_vec);
     IPR_LAUNCH_CHECK();
     return IPR_OK;

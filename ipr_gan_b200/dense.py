@@ -186,7 +186,7 @@ class Plan(object):
             tiles = L.ipr_tapgemm_m_tiles(ctypes.byref(d))
             if tiles < 0:
                 check(tiles, "ipr_tapgemm_m_tiles")
-            stats = torch.empty(tiles * self.n_phases * 4, 2, self.n_total, device=a.device, dtype=torch.float32)
+            stats = torch.empty(tiles * self.n_phases, 2, self.n_total, device=a.device, dtype=torch.float32)
             d.stats = stats.data_ptr()
         ev = _prof_begin()
         check(L.ipr_tapgemm_bf16(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),

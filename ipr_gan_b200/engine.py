@@ -95,12 +95,13 @@ def bn_apply_relu(x, scale, shift):
     return y
 
 
-def bn_relu_bwd(dy, xraw, act, gamma, mean, rstd, dgamma, dbeta, accumulate, sign=None, gamma0=0.0, sign_scale=0.0):
+def bn_relu_bwd(dy, xraw, scale, shift, gamma, mean, rstd, dgamma, dbeta, accumulate, sign=None, gamma0=0.0,
+                sign_scale=0.0):
     C = dy.shape[-1]
     nbytes = lib().ipr_bn_bwd_workspace_bytes(C)
     ws = torch.empty(nbytes // 4, device=dy.device, dtype=torch.float32)
     dx = torch.empty_like(dy)
-    check(lib().ipr_bn_relu_bwd_bf16(_p(dy), _p(xraw), _p(act), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgamma),
+    check(lib().ipr_bn_relu_bwd_bf16(_p(dy), _p(xraw), _p(scale), _p(shift), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgamma),
                                      _p(dbeta), int(bool(accumulate)), _p(sign), float(gamma0), float(sign_scale),
                                      _p(ws), nbytes, dy.numel() // C, C, _st()), "ipr_bn_relu_bwd_bf16")
     return dx
@@ -341,7 +342,7 @@ class _GeneratorFn(torch.autograd.Function):
         fcb = fc_b.detach()[perm]
         h, _ = P.fc.run(a0, P.packs.get("fc"), epi=dense.EPI_BIAS_LRELU, slope=0.0, bias=fcb)
         acts = [h.view(B, mg, mg, 512)]
-        raws, means, rstds = [], [], []
+        raws, means, rstds, scales, shifts = [], [], [], [], []
         ctx.eval_stats = False
         for i in range(3):
             bn = bns[i]
@@ -361,9 +362,11 @@ class _GeneratorFn(torch.autograd.Function):
             raws.append(raw)
             means.append(mean)
             rstds.append(rstd)
+            scales.append(scale)
+            shifts.append(shift)
         out, _ = P.last.run(acts[-1], P.packs.get("ct3"), epi=dense.EPI_TANH_NCHW, n_valid=3)
         ctx.module = module
-        ctx.save_for_backward(a0, out, fc_w, w1, w2, w3, w4, g1, g2, g3, *acts, *raws, *means, *rstds)
+        ctx.save_for_backward(a0, out, fc_w, w1, w2, w3, w4, g1, g2, g3, *acts, *raws, *means, *rstds, *scales, *shifts)
         return out
 
     @staticmethod
@@ -373,6 +376,7 @@ class _GeneratorFn(torch.autograd.Function):
         sv = ctx.saved_tensors
         a0, out, fc_w, w1, w2, w3, w4, g1, g2, g3 = sv[:10]
         acts, raws, means, rstds = sv[10:14], sv[14:17], sv[17:20], sv[20:23]
+        scales, shifts = sv[23:26], sv[26:29]
         cts, gammas = (w1, w2, w3), (g1, g2, g3)
         if ctx.eval_stats:
             raise RuntimeError("generator backward in eval mode (running statistics) is not on the training path")
@@ -396,7 +400,7 @@ class _GeneratorFn(torch.autograd.Function):
             sg, g0, sc = (None, 0.0, 0.0)
             if sign_hook is not None:
                 sg, g0, sc = sign_hook(i)
-            dx = bn_relu_bwd(d_act, raws[i], acts[i + 1], gammas[i], means[i], rstds[i], dg_t, db_t, acc_g, sg, g0, sc)
+            dx = bn_relu_bwd(d_act, raws[i], scales[i], shifts[i], gammas[i], means[i], rstds[i], dg_t, db_t, acc_g, sg, g0, sc)
             dw_t, acc_w, dws[i] = _grad_dst(mod_c[i][0].weight)
             P.ct_wg[i].run(dx, acts[i], dw_t, accumulate=acc_w)
             wd = P.packs.get("ct%d_dg" % i)

@@ -157,7 +157,7 @@ def test_layer_kernels_exact():
     yref2 = F.relu(copy.deepcopy(ref_bn)(x32.detach().clone().requires_grad_(True)))
     dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
     sign = torch.sign(torch.randn(C, device="cuda"))
-    dx = engine.bn_relu_bwd(dyb, raw, act, bn.weight.detach(), mean, rstd, dg, db, False, sign, 0.1, 2.0)
+    dx = engine.bn_relu_bwd(dyb, raw, scale, shift, bn.weight.detach(), mean, rstd, dg, db, False, sign, 0.1, 2.0)
     x2 = raw.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
     bn2 = torch.nn.BatchNorm2d(C).cuda()
     bn2.load_state_dict(ref_bn.state_dict())
