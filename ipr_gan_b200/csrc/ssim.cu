@@ -313,6 +313,171 @@ ssim_tile_kernel(const SsimParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// 32x32 planes (the DCGAN / CIFAR shape): one WARP owns one plane through all four passes, so there is no block
+// barrier at all -- warps only __syncwarp() between passes and drift apart, overlapping one plane's loads with
+// another's arithmetic.  Lane = column (vertical passes) or row (horizontal passes); every pass is a fully unrolled
+// 1-D filter over a whole line kept in registers (each shared-memory value is read exactly once), zero taps of the
+// transposed filters are dropped at compile time, and the paired quantities ((x,y), (x^2+y^2, xy), (dS/dp, dS/dq))
+// go through Blackwell's packed fma.rn.f32x2 (two fp32 FMAs per issue slot).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
+constexpr int S32_P_PITCH = 33;                  // float2 per row of the (x,y) plane
+constexpr int S32_D_PITCH = 23;                  // elements per row of the 22-wide maps
+constexpr int S32_WARP_FLOATS = 2 * 32 * S32_D_PITCH + 32 * S32_D_PITCH      // region A: P (2*32*33) or E (pq + r)
+                                + 2 * 2 * 22 * S32_P_PITCH                   // region B: Va, Vb
+                                + 2 * 22 * S32_D_PITCH + 22 * S32_D_PITCH + 6; // region C: Dpq, Dr
+static_assert(2 * 32 * S32_D_PITCH + 32 * S32_D_PITCH >= 2 * 32 * S32_P_PITCH, "E must cover P");
+
+template <bool WITH_GRAD>
+__global__ void __launch_bounds__(128)
+ssim32_warp_kernel(const SsimParams p)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *base = smem + warp * S32_WARP_FLOATS;
+    float2 *P = reinterpret_cast<float2 *>(base);                                 // [32][33]  (x, y)
+    float2 *Epq = reinterpret_cast<float2 *>(base);                               // [32][23]  aliases P (dead after pass 1)
+    float *Er = base + 2 * 32 * S32_D_PITCH;                                      // [32][23]
+    float2 *Va = reinterpret_cast<float2 *>(base + 2 * 32 * S32_D_PITCH + 32 * S32_D_PITCH + ((32 * S32_D_PITCH) & 1));
+    float2 *Vb = Va + 22 * S32_P_PITCH;                                           // [22][33] each
+    float2 *Dpq = Vb + 22 * S32_P_PITCH;                                          // [22][23]
+    float *Dr = reinterpret_cast<float *>(Dpq + 22 * S32_D_PITCH);                // [22][23]
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    float2 g2[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) g2[k] = make_float2(kTap[k], kTap[k]);
+    auto tap2 = [&](int k) { return g2[k <= 5 ? k : 10 - k]; };
+
+    for (long long plane = (long long)blockIdx.x * (blockDim.x >> 5) + warp; plane < p.planes; plane += warps_total) {
+        const float *xg = p.x + plane * 1024, *yg = p.y + plane * 1024;
+        // ---- phase 0: 8 + 8 coalesced 128-bit loads per lane, interleave into (x, y) pairs
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int v4 = it * 32 + lane;                     // float4 index inside the plane
+            float4 a = ipr_ldg_stream4(reinterpret_cast<const float4 *>(xg) + v4);
+            float4 b = ipr_ldg_stream4(reinterpret_cast<const float4 *>(yg) + v4);
+            if (p.normalized) {
+                a.x = (a.x + 1.f) * .5f; a.y = (a.y + 1.f) * .5f; a.z = (a.z + 1.f) * .5f; a.w = (a.w + 1.f) * .5f;
+                b.x = (b.x + 1.f) * .5f; b.y = (b.y + 1.f) * .5f; b.z = (b.z + 1.f) * .5f; b.w = (b.w + 1.f) * .5f;
+            }
+            float2 *dst = P + (v4 >> 3) * S32_P_PITCH + ((v4 & 7) << 2);
+            dst[0] = make_float2(a.x, b.x); dst[1] = make_float2(a.y, b.y);
+            dst[2] = make_float2(a.z, b.z); dst[3] = make_float2(a.w, b.w);
+        }
+        __syncwarp();
+        // ---- pass 1: vertical, lane = column
+        {
+            float2 w[32], q[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                w[r] = P[r * S32_P_PITCH + lane];
+                q[r] = make_float2(fmaf(w[r].x, w[r].x, w[r].y * w[r].y), w[r].x * w[r].y);
+            }
+#pragma unroll
+            for (int i = 0; i < 22; i++) {
+                float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) { a = ffma2(tap2(k), w[i + k], a); b = ffma2(tap2(k), q[i + k], b); }
+                Va[i * S32_P_PITCH + lane] = a;
+                Vb[i * S32_P_PITCH + lane] = b;
+            }
+        }
+        __syncwarp();
+        // ---- pass 2: horizontal + SSIM map + derivatives, lane = row (22 active)
+        float ssum = 0.f;
+        if (lane < 22) {
+            float2 wa[32], wb[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) { wa[c] = Va[lane * S32_P_PITCH + c]; wb[c] = Vb[lane * S32_P_PITCH + c]; }
+#pragma unroll
+            for (int j = 0; j < 22; j++) {
+                float2 m = make_float2(0.f, 0.f), e = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) { m = ffma2(tap2(k), wa[j + k], m); e = ffma2(tap2(k), wb[j + k], e); }
+                const float mx = m.x, my = m.y;
+                const float mxx = mx * mx, myy = my * my, mxy = mx * my;
+                const float A1 = 2.f * mxy + SSIM_C1;
+                const float B1 = mxx + myy + SSIM_C1;
+                const float A2 = 2.f * (e.y - mxy) + SSIM_C2;
+                const float B2 = (e.x - mxx - myy) + SSIM_C2;
+                const float iB1 = 1.0f / B1, iB2 = 1.0f / B2;
+                const float iB12 = iB1 * iB2;
+                const float S = A1 * A2 * iB12;
+                ssum += S;
+                if (WITH_GRAD) {
+                    Dpq[lane * S32_D_PITCH + j] = make_float2(2.f * my * (A2 - A1) * iB12 + 2.f * mx * S * (iB2 - iB1), -S * iB2);
+                    Dr[lane * S32_D_PITCH + j] = 2.f * A1 * iB12;
+                }
+            }
+        }
+        ssum = ipr_warp_sum(ssum);
+        if (lane == 0) p.partial[plane] = ssum;
+        if (!WITH_GRAD) { __syncwarp(); continue; }
+        __syncwarp();
+        // ---- pass 3: vertical transposed, lane = map column (22 active); zero taps dropped at compile time
+        if (lane < 22) {
+            float2 d[22]; float dr[22];
+#pragma unroll
+            for (int i = 0; i < 22; i++) { d[i] = Dpq[i * S32_D_PITCH + lane]; dr[i] = Dr[i * S32_D_PITCH + lane]; }
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                float2 a = make_float2(0.f, 0.f); float b = 0.f;
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    const int i = r - k;
+                    if (i >= 0 && i < 22) { a = ffma2(tap2(k), d[i], a); b = fmaf(kTap[k], dr[i], b); }
+                }
+                Epq[r * S32_D_PITCH + lane] = a;
+                Er[r * S32_D_PITCH + lane] = b;
+            }
+        }
+        __syncwarp();
+        // ---- pass 4: horizontal transposed + epilogue, lane = row
+        {
+            float2 e[22]; float er[22];
+#pragma unroll
+            for (int j = 0; j < 22; j++) { e[j] = Epq[lane * S32_D_PITCH + j]; er[j] = Er[lane * S32_D_PITCH + j]; }
+            float *dxr = p.dx + plane * 1024 + lane * 32;
+            const float4 *xr = reinterpret_cast<const float4 *>(xg + lane * 32);
+            const float4 *yr = reinterpret_cast<const float4 *>(yg + lane * 32);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++) {
+                float4 xv = __ldg(xr + c4), yv = __ldg(yr + c4);       // L2 hits: this warp streamed them in phase 0
+                if (p.normalized) {
+                    xv.x = (xv.x + 1.f) * .5f; xv.y = (xv.y + 1.f) * .5f; xv.z = (xv.z + 1.f) * .5f; xv.w = (xv.w + 1.f) * .5f;
+                    yv.x = (yv.x + 1.f) * .5f; yv.y = (yv.y + 1.f) * .5f; yv.z = (yv.z + 1.f) * .5f; yv.w = (yv.w + 1.f) * .5f;
+                }
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+                float o[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int c = c4 * 4 + u;
+                    float2 f = make_float2(0.f, 0.f); float fr = 0.f;
+#pragma unroll
+                    for (int k = 0; k <= RAD; k++) {
+                        const int j = c - k;
+                        if (j >= 0 && j < 22) { f = ffma2(tap2(k), e[j], f); fr = fmaf(kTap[k], er[j], fr); }
+                    }
+                    o[u] = p.coef * (f.x + 2.f * xs[u] * f.y + ys[u] * fr);
+                }
+                ipr_stg_stream4(reinterpret_cast<float4 *>(dxr) + c4, make_float4(o[0], o[1], o[2], o[3]));
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // loss = 1 - (sum of all partials) / count        (single CTA, fixed order)
 __global__ void __launch_bounds__(1024)
 ssim_finalize_loss_kernel(const float *__restrict__ partial, long long n, float inv_count, float *__restrict__ loss)
@@ -381,8 +546,34 @@ int check_common(const float *x, const float *y, int64_t batch, int C, int H, in
 }
 
 template <bool WITH_GRAD>
+int launch_warp32(const SsimParams &p, cudaStream_t st)
+{
+    constexpr int WARPS = 4;
+    const size_t smem = (size_t)WARPS * S32_WARP_FLOATS * sizeof(float);
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[WITH_GRAD]) {
+        cudaError_t e = cudaFuncSetAttribute(ssim32_warp_kernel<WITH_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_done[WITH_GRAD] = true;
+    }
+    long long ctas = (p.planes + WARPS - 1) / WARPS;
+    const long long cap = (long long)ipr_sm_count() * 2;          // 2 CTAs (8 warps) per SM, persistent over planes
+    if (ctas > cap) ctas = cap;
+    ssim32_warp_kernel<WITH_GRAD><<<(unsigned)ctas, WARPS * 32, smem, st>>>(p);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+inline bool use_warp32(const SsimParams &p) {
+    return p.H == 32 && p.W == 32 && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y) |
+                                      reinterpret_cast<uintptr_t>(p.dx)) & 15) == 0;
+}
+
+template <bool WITH_GRAD>
 int launch_tiles(const SsimParams &p, const Plan &pl, cudaStream_t st)
 {
+    if (use_warp32(p)) return launch_warp32<WITH_GRAD>(p, st);
     static bool attr_done[2] = {false, false};
     if (!attr_done[WITH_GRAD]) {
         cudaError_t e = cudaFuncSetAttribute(ssim_tile_kernel<WITH_GRAD>,
