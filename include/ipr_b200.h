@@ -281,12 +281,12 @@ int ipr_dfc_fwd_bf16(const void *a, const float *w, const float *sigma, const fl
 int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigma, const float *dlogit, void *da, float *dw,
                      int accumulate_dw, float slope, int batch, int k, ipr_stream_t stream);
 
-/* Column sums: out[c] (+)= scale * sum_r in[r][c].  `_partials_f32` reduces fp32 partial rows (the GEMM epilogue's
+/* Column sums: out[c] (+)= scale * sum_r in[r*row_stride + c], c < ncols.  `_partials_f32` reduces fp32 partial rows (the GEMM epilogue's
  * per-warp column statistics); `_bf16` reduces an NHWC bf16 tensor over its pixels (bias gradients).
  * Two launches each, fixed summation order (deterministic).  Workspace: ipr_colsum_workspace_bytes(ncols). */
 size_t ipr_colsum_workspace_bytes(int ncols);
-int ipr_colsum_partials_f32(const float *partial, int rows, int ncols, float *out, int accumulate, float scale,
-                            void *workspace, size_t workspace_bytes, ipr_stream_t stream);
+int ipr_colsum_partials_f32(const float *partial, int rows, int ncols, int row_stride, float *out, int accumulate,
+                            float scale, void *workspace, size_t workspace_bytes, ipr_stream_t stream);
 int ipr_colsum_bf16(const void *x, int64_t rows, int channels, float *out, int accumulate, float scale,
                     void *workspace, size_t workspace_bytes, ipr_stream_t stream);
 

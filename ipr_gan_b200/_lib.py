@@ -65,7 +65,7 @@ SIGNATURES = {
     "ipr_dfc_fwd_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr]),
     "ipr_dfc_bwd_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32, c_int, c_int, c_ptr]),
     "ipr_colsum_workspace_bytes": (c_size, [c_int]),
-    "ipr_colsum_partials_f32": (c_int, [c_ptr, c_int, c_int, c_ptr, c_int, c_f32, c_ptr, c_size, c_ptr]),
+    "ipr_colsum_partials_f32": (c_int, [c_ptr, c_int, c_int, c_int, c_ptr, c_int, c_f32, c_ptr, c_size, c_ptr]),
     "ipr_colsum_bf16": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_f32, c_ptr, c_size, c_ptr]),
     "ipr_sn_scratch_floats": (c_size, [c_int, c_int]),
     "ipr_sn_power_iter_f32": (c_int, [c_ptr, c_int, c_int, c_f32, c_ptr, c_ptr]),

@@ -179,23 +179,23 @@ bn_bwd_reduce_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xra
 // pass 1b: dbeta, dgamma (+ sign-loss gradient) and the per-channel coefficients of pass 2.
 //   dx = a[c] * g + b[c] * xraw + d[c]   with  a = gamma*rstd,  b = -gamma*rstd^2*dgamma_bn/M,
 //   d = -a*dbeta/M - b*mean
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float *__restrict__ partial, int rows, int C, double count,
                        const float *__restrict__ gamma, const float *__restrict__ mean, const float *__restrict__ rstd,
                        float *__restrict__ dgamma, float *__restrict__ dbeta, int accumulate,
                        const float *__restrict__ sign, float gamma0, float sign_scale,
                        float *__restrict__ coef)
 {
-    __shared__ double s1[8][33], s2[8][33];
+    __shared__ double s1[32][33], s2[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     double sg = 0.0, sx = 0.0;
     if (c < C)
-        for (int r = ty; r < rows; r += 8) { sg += (double)partial[(size_t)r * 2 * C + c]; sx += (double)partial[(size_t)r * 2 * C + C + c]; }
+        for (int r = ty; r < rows; r += 32) { sg += (double)partial[(size_t)r * 2 * C + c]; sx += (double)partial[(size_t)r * 2 * C + C + c]; }
     s1[ty][tx] = sg; s2[ty][tx] = sx;
     __syncthreads();
     if (ty != 0 || c >= C) return;
-    for (int y = 1; y < 8; y++) { sg += s1[y][tx]; sx += s2[y][tx]; }
+    for (int y = 1; y < 32; y++) { sg += s1[y][tx]; sx += s2[y][tx]; }
     const float g = gamma[c], rs = rstd[c], mu = mean[c];
     float dg = (float)sx;
     const float a = g * rs;
@@ -234,22 +234,22 @@ bn_bwd_apply_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xraw
 }
 
 // ------------------------------------------------------------------------------------ final Linear(K -> 1)
-// logits[b] = dot(a[b,:], w) / sigma + bias          one warp per sample
+// logits[b] = dot(a[b,:], w) / sigma + bias          one CTA per sample (fixed-order block reduction)
 __global__ void __launch_bounds__(256)
 dfc_fwd_kernel(const uint4 *__restrict__ a, const float *__restrict__ w, const float *__restrict__ sigma,
                const float *__restrict__ bias, float *__restrict__ logits, int batch, int k_vec)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= batch) return;
+    __shared__ float red[32];
+    const int b = blockIdx.x;
     float acc = 0.0f;
-    for (int i = lane; i < k_vec; i += 32) {
+    for (int i = threadIdx.x; i < k_vec; i += blockDim.x) {
         float f[8];
-        unpack8(__ldg(a + (size_t)warp * k_vec + i), f);
+        unpack8(__ldg(a + (size_t)b * k_vec + i), f);
         const float4 w0 = __ldg(reinterpret_cast<const float4 *>(w) + 2 * i), w1 = __ldg(reinterpret_cast<const float4 *>(w) + 2 * i + 1);
         acc += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z + f[7] * w1.w;
     }
-    acc = ipr_warp_sum(acc);
-    if (lane == 0) logits[warp] = acc / (sigma ? *sigma : 1.0f) + (bias ? *bias : 0.0f);
+    acc = ipr_block_sum(acc, red);
+    if (threadIdx.x == 0) logits[b] = acc / (sigma ? *sigma : 1.0f) + (bias ? *bias : 0.0f);
 }
 
 // da[b,k] = dlogit[b] * w[k] / sigma * lrelu'(a[b,k])      (gradient w.r.t. the previous conv's pre-activation)
@@ -378,7 +378,7 @@ extern "C" int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const floa
     bn_bwd_reduce_kernel<<<(unsigned)ctas, 256, smem, st>>>((const uint4 *)dy, (const uint4 *)xraw, scale, shift,
                                                             mean, rstd, rows, c_vec, partial);
     IPR_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<(channels + 31) / 32, 256, 0, st>>>(partial, (int)ctas, channels, (double)rows, gamma, mean,
+    bn_bwd_finalize_kernel<<<(channels + 31) / 32, 1024, 0, st>>>(partial, (int)ctas, channels, (double)rows, gamma, mean,
                                                                   rstd, dgamma, dbeta, accumulate, sign, gamma0,
                                                                   sign_scale, coef);
     IPR_LAUNCH_CHECK();
@@ -395,7 +395,7 @@ extern "C" int ipr_dfc_fwd_bf16(const void *a, const float *w, const float *sigm
     IPR_REQUIRE(a && w && logits, IPR_E_NULL);
     IPR_REQUIRE(batch > 0 && k > 0 && k % 8 == 0, IPR_E_SHAPE);
     IPR_REQUIRE(ipr_aligned16(a) && ipr_aligned16(w), IPR_E_ALIGN);
-    dfc_fwd_kernel<<<(batch * 32 + 255) / 256, 256, 0, ipr_cu(stream)>>>((const uint4 *)a, w, sigma, bias, logits, batch, k / 8);
+    dfc_fwd_kernel<<<batch, 256, 0, ipr_cu(stream)>>>((const uint4 *)a, w, sigma, bias, logits, batch, k / 8);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -425,20 +425,39 @@ namespace {
 // stage 1: out[g][c] = sum over the rows assigned to group g of in[r][c]   (fp32 partial rows, e.g. GEMM-epilogue
 // statistics).  CTA = 32 columns x 8 row lanes; grid = (ncols/32, G).
 __global__ void __launch_bounds__(256)
-colsum_partials_stage1(const float *__restrict__ in, int rows, int ncols, float *__restrict__ out)
+colsum_partials_stage1(const float *__restrict__ in, int rows, int ncols, int row_stride, float *__restrict__ out)
 {
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     float acc = 0.0f;
     if (c < ncols)
-        for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) acc += in[(size_t)r * ncols + c];
+        for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) acc += in[(size_t)r * row_stride + c];
     sm[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && c < ncols) {
 #pragma unroll
         for (int y = 1; y < 8; y++) acc += sm[y][tx];
         out[(size_t)blockIdx.y * ncols + c] = acc;
+    }
+}
+// few rows: out[c] (+)= scale * sum_r in[r][c] in one launch (32 columns x 8 row lanes per CTA, fixed order)
+__global__ void __launch_bounds__(256)
+colsum_small_kernel(const float *__restrict__ in, int rows, int ncols, int row_stride, float *__restrict__ out,
+                    int accumulate, float scale)
+{
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float acc = 0.0f;
+    if (c < ncols)
+        for (int r = ty; r < rows; r += 8) acc += in[(size_t)r * row_stride + c];
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < ncols) {
+#pragma unroll
+        for (int y = 1; y < 8; y++) acc += sm[y][tx];
+        out[c] = accumulate ? out[c] + acc * scale : acc * scale;
     }
 }
 // stage 2: out[c] (+)= scale * sum_g in[g][c], double accumulation, fixed order
@@ -477,15 +496,22 @@ colsum_bf16_stage1(const uint4 *__restrict__ x, long long rows, int c_vec, float
 
 extern "C" size_t ipr_colsum_workspace_bytes(int ncols) { return (size_t)64 * ncols * sizeof(float); }
 
-extern "C" int ipr_colsum_partials_f32(const float *partial, int rows, int ncols, float *out, int accumulate,
-                                       float scale, void *workspace, size_t workspace_bytes, ipr_stream_t stream)
+extern "C" int ipr_colsum_partials_f32(const float *partial, int rows, int ncols, int row_stride, float *out,
+                                       int accumulate, float scale, void *workspace, size_t workspace_bytes,
+                                       ipr_stream_t stream)
 {
+    IPR_REQUIRE(row_stride >= ncols, IPR_E_SHAPE);
     IPR_REQUIRE(partial && out && workspace, IPR_E_NULL);
     IPR_REQUIRE(rows > 0 && ncols > 0, IPR_E_SHAPE);
     IPR_REQUIRE(workspace_bytes >= ipr_colsum_workspace_bytes(ncols), IPR_E_WORKSPACE);
+    if (rows <= 256) {                      // few rows: one launch, every CTA reduces its 32 columns completely
+        colsum_small_kernel<<<(ncols + 31) / 32, 256, 0, ipr_cu(stream)>>>(partial, rows, ncols, row_stride, out, accumulate, scale);
+        IPR_LAUNCH_CHECK();
+        return IPR_OK;
+    }
     const int G = rows < 8 * 64 ? (rows + 7) / 8 : 64;
     dim3 grid((ncols + 31) / 32, G);
-    colsum_partials_stage1<<<grid, 256, 0, ipr_cu(stream)>>>(partial, rows, ncols, (float *)workspace);
+    colsum_partials_stage1<<<grid, 256, 0, ipr_cu(stream)>>>(partial, rows, ncols, row_stride, (float *)workspace);
     IPR_LAUNCH_CHECK();
     colsum_stage2<<<(ncols + 255) / 256, 256, 0, ipr_cu(stream)>>>((const float *)workspace, G, ncols, out, accumulate, scale);
     IPR_LAUNCH_CHECK();

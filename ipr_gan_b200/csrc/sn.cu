@@ -103,18 +103,35 @@ sn_u_sigma_kernel(const __grid_constant__ SnTable tab, const float *__restrict__
     }
 }
 
-// C1: per-CTA partial of <G, W>;  C2: G <- (G - (<G,W>/sigma) u v^T) / sigma   (in place)
-constexpr int DOT_CTAS = 32;
+// C1: per-CTA partial of <G, W> (each CTA covers DOT_SPAN elements with 128-bit loads);
+// C2: G <- (G - (<G,W>/sigma) u v^T) / sigma   (in place, or added into grad_out)
+constexpr int DOT_SPAN = 256 * 16;
 
 __global__ void __launch_bounds__(256)
 sn_dot_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
 {
     __shared__ float red[32];
-    const int l = blockIdx.x / DOT_CTAS, part = blockIdx.x - l * DOT_CTAS;
+    const int l = find_layer(tab, blockIdx.x);
     const ipr_sn_layer_t L = tab.layer[l];
+    const int part = blockIdx.x - tab.cta_begin[l];
     const long long n = (long long)L.rows * L.cols;
+    const long long e0 = (long long)part * DOT_SPAN;
     float acc = 0.0f;
-    for (long long i = (long long)part * 256 + threadIdx.x; i < n; i += (long long)DOT_CTAS * 256) acc += L.grad[i] * L.w[i];
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(L.grad) | reinterpret_cast<uintptr_t>(L.w)) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long i = e0 + ((long long)j * 256 + threadIdx.x) * 4;
+            if (i < n) {
+                const float4 a = *reinterpret_cast<const float4 *>(L.grad + i), b = *reinterpret_cast<const float4 *>(L.w + i);
+                acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+            }
+        }
+    } else {
+        for (int j = 0; j < 16; j++) {
+            const long long i = e0 + (long long)j * 256 + threadIdx.x;
+            if (i < n) acc += L.grad[i] * L.w[i];
+        }
+    }
     const float tot = ipr_block_sum(acc, red);
     if (threadIdx.x == 0) scratch[L.scratch_off + part] = tot;
 }
@@ -122,19 +139,25 @@ sn_dot_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
 __global__ void __launch_bounds__(256)
 sn_grad_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scratch)
 {
+    __shared__ float red[32];
     const int l = find_layer(tab, blockIdx.x);
     const ipr_sn_layer_t L = tab.layer[l];
-    float dot = 0.0f;
-    for (int k = 0; k < DOT_CTAS; k++) dot += scratch[L.scratch_off + k];
+    const long long n = (long long)L.rows * L.cols;
+    const int parts = (int)((n + DOT_SPAN - 1) / DOT_SPAN);
+    float d = 0.0f;
+    for (int k = threadIdx.x; k < parts; k += blockDim.x) d += scratch[L.scratch_off + k];
+    const float dot = ipr_block_sum(d, red);                 // same fixed order in every CTA
     const float sigma = *L.sigma;
     const float coef = dot / sigma;
     const float inv = 1.0f / sigma;
-    const long long n = (long long)L.rows * L.cols;
-    const long long i = (long long)(blockIdx.x - tab.cta_begin[l]) * 256 + threadIdx.x;
-    if (i >= n) return;
-    const int r = (int)(i / L.cols), c = (int)(i - (long long)r * L.cols);
-    const float out = (L.grad[i] - coef * L.u[r] * L.v[c]) * inv;
-    if (L.grad_out) L.grad_out[i] += out; else L.grad[i] = out;
+    const long long base = (long long)(blockIdx.x - tab.cta_begin[l]) * DOT_SPAN;
+    for (int j = 0; j < 16; j++) {
+        const long long i = base + (long long)j * 256 + threadIdx.x;
+        if (i >= n) break;
+        const int r = (int)(i / L.cols), c = (int)(i - (long long)r * L.cols);
+        const float out = (L.grad[i] - coef * L.u[r] * L.v[c]) * inv;
+        if (L.grad_out) L.grad_out[i] += out; else L.grad[i] = out;
+    }
 }
 
 int fill(SnTable &t, const ipr_sn_layer_t *layers, int n)
@@ -155,7 +178,8 @@ int fill(SnTable &t, const ipr_sn_layer_t *layers, int n)
 extern "C" size_t ipr_sn_scratch_floats(int rows, int cols)
 {
     const size_t a = (size_t)((rows + ROW_CHUNK - 1) / ROW_CHUNK) * cols;
-    const size_t b = (size_t)rows > (size_t)DOT_CTAS ? (size_t)rows : (size_t)DOT_CTAS;
+    const size_t parts = ((size_t)rows * cols + DOT_SPAN - 1) / DOT_SPAN;
+    const size_t b = (size_t)rows > parts ? (size_t)rows : parts;
     return (a > b ? a : b) + 32;
 }
 
@@ -198,14 +222,14 @@ extern "C" int ipr_sn_weight_grad_f32(const ipr_sn_layer_t *layers_host, int n_l
     IPR_REQUIRE(scratch, IPR_E_NULL);
     for (int i = 0; i < n_layers; i++) IPR_REQUIRE(t.layer[i].grad, IPR_E_NULL);
     cudaStream_t st = ipr_cu(stream);
-    sn_dot_kernel<<<n_layers * DOT_CTAS, 256, 0, st>>>(t, scratch);
-    IPR_LAUNCH_CHECK();
     int total = 0;
     for (int i = 0; i < n_layers; i++) {
         t.cta_begin[i] = total;
-        total += (int)(((long long)t.layer[i].rows * t.layer[i].cols + 255) / 256);
+        total += (int)(((long long)t.layer[i].rows * t.layer[i].cols + DOT_SPAN - 1) / DOT_SPAN);
     }
     t.cta_begin[n_layers] = total;
+    sn_dot_kernel<<<total, 256, 0, st>>>(t, scratch);
+    IPR_LAUNCH_CHECK();
     sn_grad_kernel<<<total, 256, 0, st>>>(t, scratch);
     IPR_LAUNCH_CHECK();
     return IPR_OK;

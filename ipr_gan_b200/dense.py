@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import check, lib
 
 MAX_TAPS, MAX_PHASES = 16, 4
+_SM_COUNT_TILES = 120          # want at least this many CTA tiles before widening the N tile
 
 # When set to a list, every GEMM launch appends (kind, algorithmic_flops, start_event, end_event): bench.py uses
 # it for the live tensor-roofline measurement (CUDA events on the launching stream).
@@ -159,7 +160,14 @@ class Plan(object):
         d.a, d.a_n, d.a_h, d.a_w, d.a_c = a.data_ptr(), N, H, W, C
         d.a_parity = self.a_parity
         d.q_h, d.q_w = (H // 2, W // 2) if self.a_parity else (H, W)
-        d.b, d.n_total, d.block_n = b_packed.data_ptr(), self.n_total, self.block_n
+        # tile width: the widest N tile that still yields about one tile per SM (wide tiles re-read A least, but a
+        # few wide tiles leave most of the chip idle and serialise a long K loop -- the small-batch regime)
+        block_n = self.block_n
+        m_pix = N * ((H // 2) * (W // 2) if self.a_parity else H * W)
+        m_tiles = (m_pix + 127) // 128
+        while block_n > 64 and m_tiles * (self.n_total // block_n) * self.n_phases < _SM_COUNT_TILES:
+            block_n //= 2
+        d.b, d.n_total, d.block_n = b_packed.data_ptr(), self.n_total, block_n
         d.n_phases, d.n_taps = self.n_phases, self.n_taps
         for ph, taps in enumerate(self.taps):
             for t, (mp, dh, dw, _, _) in enumerate(taps):
@@ -214,7 +222,7 @@ class WGrad(ctypes.Structure):
 
 
 _SM_COUNT = 148
-_WGRAD_OVERSUB = int(__import__('os').environ.get('IPR_WGRAD_OVERSUB', '2'))
+_WGRAD_OVERSUB = int(__import__('os').environ.get('IPR_WGRAD_OVERSUB', '1'))
 
 
 class WGradPlan(object):

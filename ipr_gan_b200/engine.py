@@ -44,14 +44,15 @@ def im2col3(x, tanh_out=None):
     return out
 
 
-def colsum_partials(partial, out=None, accumulate=False, scale=1.0):
-    """partial: [rows][ncols] fp32 -> out[ncols] (fixed-order two-stage reduction)."""
-    rows, ncols = partial.shape[0], partial.numel() // partial.shape[0]
+def colsum_partials(partial, out=None, accumulate=False, scale=1.0, ncols=None):
+    """partial: [rows][row_stride] fp32 -> out[ncols] = column sums of the first ``ncols`` columns (fixed order)."""
+    rows, stride = partial.shape[0], partial.numel() // partial.shape[0]
+    ncols = stride if ncols is None else ncols
     if out is None:
         out = torch.empty(ncols, device=partial.device, dtype=torch.float32)
     nbytes = lib().ipr_colsum_workspace_bytes(ncols)
     ws = torch.empty(nbytes // 4, device=partial.device, dtype=torch.float32)
-    check(lib().ipr_colsum_partials_f32(_p(partial), rows, ncols, _p(out), int(bool(accumulate)), float(scale),
+    check(lib().ipr_colsum_partials_f32(_p(partial), rows, ncols, stride, _p(out), int(bool(accumulate)), float(scale),
                                         _p(ws), nbytes, _st()), "ipr_colsum_partials_f32")
     return out
 
@@ -488,7 +489,8 @@ class _DiscriminatorFn(torch.autograd.Function):
             gB[7] = dlogits.sum().view(1)
         dy = dy.view(acts[-1].shape)
         if want:
-            gB[6] = colsum_bf16(dy.view(-1, dy.shape[-1]))
+            dst, acc, gB[6] = _grad_dst(layers[6].bias)
+            colsum_bf16(dy.view(-1, dy.shape[-1]), out=dst, accumulate=acc)
         for i in range(5, -1, -1):                 # conv layers 7..2 (index i+1 in the layer list)
             li = i + 1
             if want:
@@ -498,7 +500,8 @@ class _DiscriminatorFn(torch.autograd.Function):
             dy, st = P.conv_dg[i].run(dy, P.packs.get("c%d_dg" % li), epi=dense.EPI_MASK, slope=0.1, mask=acts[i],
                                       sigma=sig[li], want_stats=want)
             if want:
-                gB[i] = colsum_partials(st)[:dy.shape[-1]]
+                dst, acc, gB[i] = _grad_dst(layers[i].bias)
+                colsum_partials(st, out=dst, accumulate=acc, ncols=dy.shape[-1])
         dx = None
         if ctx.x_needs_grad:
             dx, _ = P.first_dg.run(dy, P.packs.get("c0_dg"), epi=dense.EPI_LINEAR_NCHW, sigma=sig[0], n_valid=3)
