@@ -211,7 +211,10 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # live tensor-roofline measurement: one eager step with CUDA events around every GEMM launch
-    dense.PROFILE = []
+    tr._step()                                   # eager warm-up (allocator, lazy attributes)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(200_000_000)               # ~0.1 s GPU spin: the host enqueues the whole step behind it, so the
+    dense.PROFILE = []                           # event pairs below time back-to-back kernels, not launch gaps
     tr._step()
     torch.cuda.synchronize()
     gemm_ms = sum(a.elapsed_time(b) for _, _, a, b in dense.PROFILE)
