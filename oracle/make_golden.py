@@ -196,6 +196,65 @@ def gen_dcgan_step(ref):
     np.savez_compressed(os.path.join(GOLD, "dcgan_step.npz"), **out)
 
 
+def _wrap(models, Config, model, bbox, wbox):
+    model = models.BlackBoxWrapper(model, Config(bbox))
+    return models.WhiteBoxWrapper(model, Config(wbox))
+
+
+def gen_srgan_cyclegan_steps(ref):
+    """One protected pre-training step + one protected GAN step of IPR-SRGAN (24 -> 96, batch 2; VGG-19 with seeded random
+    weights, the pretrained file needs the network) and one protected IPR-CycleGAN step (Resnet9Blocks, 64 x 64, batch 1)
+    through the reference's own models / wrappers, driven as experiments/image_super_resolution.py:84-113 and
+    experiments/image_translation.py:90-112 do."""
+    import torchvision
+    models, networks, Config = ref["models"], ref["networks"], ref["configs"].Config
+    import networks.vgg as ref_vgg
+    ref_vgg.vgg19 = lambda pretrained=True: torchvision.models.vgg19(weights=None)
+    out = {}
+    opt = {"lr": 1.0e-4, "betas": [0.9, 0.999]}
+    torch.manual_seed(SEED)
+    sr = models.SRGAN(Config({"G": "SRResNet", "D": "Discriminator96", "V": "VGG19Feature", "opt": "Adam", "opt_param": opt,
+                              "type": "SRGAN"}), device=[torch.device("cpu")])
+    sr = _wrap(models, Config, sr,
+               {"fn_inp": {"type": "RandomNoisePatch", "size": 12}, "fn_out": {"size": 48, "opaque": True, "type": "PasteWatermark",
+                                                                              "watermark": MARK},
+                "lambda": 1.0, "loss_fn": "ssim", "normalized": False, "input_var": "low_res", "output_var": "super_res",
+                "target": "G"},
+               {"gamma_0": 0.1, "string": "EXAMPLE A", "target": "G"})
+    g = torch.Generator().manual_seed(SEED)
+    lr, hr = torch.rand(2, 3, 24, 24, generator=g), torch.rand(2, 3, 96, 96, generator=g)
+    sr.update_g({"low_res": lr, "high_res": hr, "pretrain": True, "inhibit_bbox": True})
+    m0 = sr.get_metrics()
+    sr.update_g({"low_res": lr, "high_res": hr, "pretrain": False})
+    sr.update_d({"high_res": sr.high_res, "super_res": sr.super_res})
+    m1 = sr.get_metrics()
+    out["sr_pre_keys"], out["sr_pre"] = np.array(sorted(m0)), np.array([m0[k] for k in sorted(m0)])
+    out["sr_gan_keys"], out["sr_gan"] = np.array(sorted(m1)), np.array([m1[k] for k in sorted(m1)])
+    out["sr_super_res"] = t2n(sr.super_res[:1, :, :8, :8])
+    out["sr_state_keys"] = np.array(list(sr.state_dict().keys()))
+    out["sr_sign_keys"] = np.array(list(sr.state_dict()["sign"].keys())[:3])
+
+    torch.manual_seed(SEED)
+    cg = models.CycleGAN(Config({"G": "Resnet9Blocks", "D": "ConvDiscriminator", "lambda_A": 10.0, "lambda_B": 10.0,
+                                 "lambda_idt": 0.5, "opt": "Adam", "opt_param": {"lr": 2.0e-4, "betas": [0.5, 0.999]},
+                                 "pool_size": 50, "epoch": 200, "type": "CycleGAN"}), device=[torch.device("cpu")])
+    cg = _wrap(models, Config, cg,
+               {"fn_inp": {"type": "RandomNoisePatch", "size": 32}, "fn_out": {"size": 32, "opaque": True, "type": "PasteWatermark",
+                                                                              "watermark": MARK},
+                "lambda": 1.0, "loss_fn": "ssim", "normalized": True, "input_var": "real_B", "output_var": "fake_A",
+                "target": "GB"},
+               {"gamma_0": 0.1, "string": "EXAMPLE A", "target": "GB"})
+    a, b = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1, torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
+    cg.update_g({"real_A": a, "real_B": b})
+    cg.update_d({"real_A": cg.real_A, "real_B": cg.real_B, "fake_A": cg.fake_A.detach(), "fake_B": cg.fake_B.detach()})
+    m2 = cg.get_metrics()
+    out["cg_keys"], out["cg"] = np.array(sorted(m2)), np.array([m2[k] for k in sorted(m2)])
+    out["cg_fake_A"] = t2n(cg.fake_A[:1, :, :8, :8])
+    out["cg_state_keys"] = np.array(list(cg.state_dict().keys()))
+    out["cg_ber"] = t2n(cg.loss_model.compute_ber(cg.GB))
+    np.savez_compressed(os.path.join(GOLD, "srgan_cyclegan_steps.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)  # summation order of CPU reductions must not depend on the thread count
@@ -205,6 +264,7 @@ def main():
         gen_sign(ref)
         gen_phash(ref)
         gen_dcgan_step(ref)
+        gen_srgan_cyclegan_steps(ref)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

@@ -1,0 +1,82 @@
+"""GPU: protected IPR-SRGAN (config 3 shape: 24 -> 96) and IPR-CycleGAN (config 4: Resnet9Blocks, InstanceNorm sign
+loss) steps through the drop-in models / wrappers against metrics recorded from the UNMODIFIED reference
+(tests/golden/srgan_cyclegan_steps.npz, oracle/make_golden.py).  The dense layers of these two families still run as
+fp32 PyTorch ops (see networks/torch_nets.py); triggers, SSIM watermark loss and sign loss run on the sm_100a kernels.
+Tolerance 5e-3: fp32 cuDNN vs fp32 MKL-DNN convolution algorithms through 30-50 layers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+SEED = 1234
+
+
+def _cfg(d):
+    from configs import Config
+    return Config(d)
+
+
+def _close(got, keys, want, tol=5e-3):
+    assert sorted(got) == [str(k) for k in keys]
+    for k, w in zip(keys, want):
+        g = got[str(k)]
+        assert abs(g - w) <= tol * max(1.0, abs(w)), (str(k), g, w)
+
+
+def test_srgan_protected_steps(golden, watermark_path):
+    import models
+    os.environ["IPR_VGG_RANDOM_INIT"] = "1"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = golden("srgan_cyclegan_steps")
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(SEED)
+    sr = models.SRGAN(_cfg({"G": "SRResNet", "D": "Discriminator96", "V": "VGG19Feature", "opt": "Adam",
+                            "opt_param": {"lr": 1.0e-4, "betas": [0.9, 0.999]}, "type": "SRGAN"}), device=[dev])
+    sr = models.BlackBoxWrapper(sr, _cfg({"fn_inp": {"type": "RandomNoisePatch", "size": 12},
+                                          "fn_out": {"size": 48, "opaque": True, "type": "PasteWatermark",
+                                                     "watermark": watermark_path},
+                                          "lambda": 1.0, "loss_fn": "ssim", "normalized": False, "input_var": "low_res",
+                                          "output_var": "super_res", "target": "G"}))
+    sr = models.WhiteBoxWrapper(sr, _cfg({"gamma_0": 0.1, "string": "EXAMPLE A", "target": "G"}))
+    gen = torch.Generator().manual_seed(SEED)
+    lr, hr = torch.rand(2, 3, 24, 24, generator=gen), torch.rand(2, 3, 96, 96, generator=gen)
+    sr.update_g({"low_res": lr, "high_res": hr, "pretrain": True, "inhibit_bbox": True})
+    _close(sr.get_metrics(), g["sr_pre_keys"], g["sr_pre"])
+    sr.update_g({"low_res": lr, "high_res": hr, "pretrain": False})
+    sr.update_d({"high_res": sr.high_res, "super_res": sr.super_res})
+    _close(sr.get_metrics(), g["sr_gan_keys"], g["sr_gan"])
+    assert np.allclose(sr.super_res[:1, :, :8, :8].detach().cpu().numpy(), g["sr_super_res"], atol=5e-3)
+    assert list(sr.state_dict().keys()) == [str(k) for k in g["sr_state_keys"]]
+    assert list(sr.state_dict()["sign"].keys())[:3] == [str(k) for k in g["sr_sign_keys"]]
+    assert sr.loss_model.compute_ber_counts(sr.G) == (0, 33 * 64)          # 2 112 signature bits in 33 BatchNorm layers
+
+
+def test_cyclegan_protected_step(golden, watermark_path):
+    import models
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = golden("srgan_cyclegan_steps")
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(SEED)
+    cg = models.CycleGAN(_cfg({"G": "Resnet9Blocks", "D": "ConvDiscriminator", "lambda_A": 10.0, "lambda_B": 10.0,
+                               "lambda_idt": 0.5, "opt": "Adam", "opt_param": {"lr": 2.0e-4, "betas": [0.5, 0.999]},
+                               "pool_size": 50, "epoch": 200, "type": "CycleGAN"}), device=[dev])
+    cg = models.BlackBoxWrapper(cg, _cfg({"fn_inp": {"type": "RandomNoisePatch", "size": 32},
+                                          "fn_out": {"size": 32, "opaque": True, "type": "PasteWatermark",
+                                                     "watermark": watermark_path},
+                                          "lambda": 1.0, "loss_fn": "ssim", "normalized": True, "input_var": "real_B",
+                                          "output_var": "fake_A", "target": "GB"}))
+    cg = models.WhiteBoxWrapper(cg, _cfg({"gamma_0": 0.1, "string": "EXAMPLE A", "target": "GB"}))
+    gen = torch.Generator().manual_seed(SEED)
+    for _ in range(2):                                   # the SRGAN fixture consumed these draws first
+        torch.rand(2, 3, 24, 24, generator=gen) if _ == 0 else torch.rand(2, 3, 96, 96, generator=gen)
+    a, b = torch.rand(1, 3, 64, 64, generator=gen) * 2 - 1, torch.rand(1, 3, 64, 64, generator=gen) * 2 - 1
+    cg.update_g({"real_A": a, "real_B": b})
+    cg.update_d({"real_A": cg.real_A, "real_B": cg.real_B, "fake_A": cg.fake_A.detach(), "fake_B": cg.fake_B.detach()})
+    _close(cg.get_metrics(), g["cg_keys"], g["cg"])
+    assert np.allclose(cg.fake_A[:1, :, :8, :8].detach().cpu().numpy(), g["cg_fake_A"], atol=5e-3)
+    assert list(cg.state_dict().keys()) == [str(k) for k in g["cg_state_keys"]]
+    assert cg.loss_model.compute_ber_counts(cg.GB) == (0, 5248)            # 23 InstanceNorm layers of Resnet9Blocks
