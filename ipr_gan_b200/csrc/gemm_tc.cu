@@ -19,6 +19,7 @@
 //   tiles (6-8 smem stages, ~190 KB).
 #include "ipr_common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -53,22 +54,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                const __grid_constant__ CUtensorMap mapB, const TgParams p)
 {
     constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    // MT = 2: the CTA tile is two 128-row sub-tiles that share ONE B (weight) tile in shared memory -- 1.36x more
+    // flops per byte streamed from L2, which is what bounds this kernel (about 10 TB/s L2->SM chip-wide)
+    constexpr int A_BYTES = MT * A_STAGE_BYTES;
+    constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
     constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;     // TMEM columns of one accumulator
-    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                     // double-buffered: epilogue(i) overlaps mainloop(i+1)
+    constexpr uint32_t BUF_COLS = MT * ACC_COLS;
+    constexpr uint32_t TMEM_COLS = 2 * BUF_COLS;                     // double-buffered: epilogue(i) overlaps mainloop(i+1)
+    static_assert(TMEM_COLS <= 512, "TMEM budget");
     constexpr int CH = BLOCK_N >= 32 ? 32 : 16;                      // columns per tcgen05.ld
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-byte alignment
     const uint32_t sA = smem_base;
-    const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+    const uint32_t sB = smem_base + STAGES * A_BYTES;
     const uint32_t bar_full = sB + STAGES * B_STAGE_BYTES;                // STAGES x 8 bytes
     const uint32_t bar_empty = bar_full + STAGES * 8;
     const uint32_t bar_acc_full = bar_empty + STAGES * 8;                 // 2 x 8
@@ -80,7 +86,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.n_taps * p.c_chunks;
     const int n_blks = p.n_total / BLOCK_N;
-    const int tiles_per_phase = p.m_tiles * n_blks;
+    const int m_groups = (p.m_tiles + MT - 1) / MT;                 // CTA tiles along M
+    const int tiles_per_phase = m_groups * n_blks;
     const int total_tiles = tiles_per_phase * p.n_phases;
 
     if (warp == 0 && lane == 0) {
@@ -103,10 +110,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             uint32_t g = 0;                                            // running k-block counter across tiles
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int phase = tile / tiles_per_phase, rem = tile - phase * tiles_per_phase;
-                const int m_tile = rem / n_blks, n_blk = rem - m_tile * n_blks;
-                int img0, h0;
-                if (p.tile_imgs == 1) { img0 = m_tile / p.tiles_per_img; h0 = (m_tile - img0 * p.tiles_per_img) * p.tile_h; }
-                else { img0 = m_tile * p.tile_imgs; h0 = 0; }
+                const int m_grp = rem / n_blks, n_blk = rem - m_grp * n_blks;
+                int img0[MT], h0[MT];
+#pragma unroll
+                for (int j = 0; j < MT; j++) {
+                    const int m_tile = m_grp * MT + j;              // a tile past the end reads zeros (TMA out-of-bounds fill)
+                    if (p.tile_imgs == 1) { img0[j] = m_tile / p.tiles_per_img; h0[j] = (m_tile - img0[j] * p.tiles_per_img) * p.tile_h; }
+                    else { img0[j] = m_tile * p.tile_imgs; h0[j] = 0; }
+                }
                 for (int kb = 0; kb < num_kb; kb++, g++) {
                     const int s = g % STAGES;
                     const uint32_t par = (g / STAGES) & 1u;
@@ -115,8 +126,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const int tap = kb / p.c_chunks, cc = kb - tap * p.c_chunks;
                     const int mi = p.tap_map[phase][tap];
                     const CUtensorMap *ma = mi == 0 ? &mapA0 : (mi == 1 ? &mapA1 : (mi == 2 ? &mapA2 : &mapA3));
-                    tma_load_4d(sA + s * A_STAGE_BYTES, ma, bar_full + 8 * s, cc * BLOCK_K, (int)p.tap_dw[phase][tap],
-                                h0 + (int)p.tap_dh[phase][tap], img0);
+#pragma unroll
+                    for (int j = 0; j < MT; j++)
+                        tma_load_4d(sA + s * A_BYTES + j * A_STAGE_BYTES, ma, bar_full + 8 * s, cc * BLOCK_K,
+                                    (int)p.tap_dw[phase][tap], h0[j] + (int)p.tap_dh[phase][tap], img0[j]);
                     tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, bar_full + 8 * s, tap * p.a_c + cc * BLOCK_K,
                                 phase * p.n_total + n_blk * BLOCK_N);
                 }
@@ -132,18 +145,22 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t buf = it & 1u;
                 mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t acc = tmem_base + buf * ACC_COLS;
+                const uint32_t acc = tmem_base + buf * BUF_COLS;
                 for (int kb = 0; kb < num_kb; kb++, g++) {
                     const int s = g % STAGES;
                     const uint32_t par = (g / STAGES) & 1u;
                     mbar_wait(bar_full + 8 * s, par);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(sA + s * A_STAGE_BYTES, 0, 1024);
                     const uint64_t db = umma_desc_sw128(sB + s * B_STAGE_BYTES, 0, 1024);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-                        // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int j = 0; j < MT; j++) {
+                            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
+                            const uint64_t da = umma_desc_sw128(sA + s * A_BYTES + j * A_STAGE_BYTES, 0, 1024);
+                            umma_bf16(acc + j * ACC_COLS, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                      (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(bar_empty + 8 * s);           // smem stage reusable once these MMAs retire
                 }
@@ -162,26 +179,29 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
             const int phase = tile / tiles_per_phase, rem = tile - phase * tiles_per_phase;
-            const int m_tile = rem / n_blks, n_blk = rem - m_tile * n_blks;
-            int img0, h0;
-            if (p.tile_imgs == 1) { img0 = m_tile / p.tiles_per_img; h0 = (m_tile - img0 * p.tiles_per_img) * p.tile_h; }
-            else { img0 = m_tile * p.tile_imgs; h0 = 0; }
-            const int img = img0 + i_img;
-            const bool valid = img < p.a_n;
-            const int oh = (h0 + i_row) * p.out_sh + p.out_oh[phase];
-            const int ow = i_col * p.out_sw + p.out_ow[phase];
-            const size_t pix = ((size_t)img * p.out_h + oh) * p.out_w + ow;
+            const int m_grp = rem / n_blks, n_blk = rem - m_grp * n_blks;
             const uint32_t buf = it & 1u;
             mbar_wait_backoff(bar_acc_full + 8 * buf, (it >> 1) & 1u);
             tc_fence_after();
 #pragma unroll 1
+          for (int sub = 0; sub < MT; sub++) {
+            const int m_tile = m_grp * MT + sub;
+            int img0, h0;
+            if (p.tile_imgs == 1) { img0 = m_tile / p.tiles_per_img; h0 = (m_tile - img0 * p.tiles_per_img) * p.tile_h; }
+            else { img0 = m_tile * p.tile_imgs; h0 = 0; }
+            const int img = img0 + i_img;
+            const bool valid = img < p.a_n && m_tile < p.m_tiles;
+            const int oh = (h0 + i_row) * p.out_sh + p.out_oh[phase];
+            const int ow = i_col * p.out_sw + p.out_ow[phase];
+            const size_t pix = ((size_t)img * p.out_h + oh) * p.out_w + ow;
+#pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
                 uint32_t raw[32];
-                const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                const uint32_t taddr = tmem_base + buf * BUF_COLS + sub * ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
                 if constexpr (CH == 32) tmem_ld_32x32(taddr, raw);
                 else tmem_ld_32x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&raw));
                 tmem_ld_wait();
-                if (c0 + CH >= BLOCK_N) {
+                if (c0 + CH >= BLOCK_N && sub == MT - 1) {
                     // last chunk is in registers: hand the accumulator back to the MMA warp before the slow part
                     tc_fence_before();
                     __syncwarp();
@@ -282,7 +302,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int t = threadIdx.x - 64;                        // 0..127 within the epilogue warps
                 float *dst = p.stats + ((size_t)phase * p.m_tiles + m_tile) * 2 * p.n_total + n_blk * BLOCK_N;
-                for (int c = t; c < 2 * BLOCK_N; c += 128) {
+                for (int c = t; c < 2 * BLOCK_N && m_tile < p.m_tiles; c += 128) {
                     const int which = c / BLOCK_N, col = c - which * BLOCK_N;
                     const float tot = stat_sm[(0 * 2 + which) * BLOCK_N + col] + stat_sm[(1 * 2 + which) * BLOCK_N + col] +
                                       stat_sm[(2 * 2 + which) * BLOCK_N + col] + stat_sm[(3 * 2 + which) * BLOCK_N + col];
@@ -290,6 +310,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+          }
         }
     }
     tc_fence_before();
@@ -297,20 +318,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MT>
 int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3 grid, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + 256 + 8 * BLOCK_N * 4 + 1024 + 64;
+    constexpr size_t smem = (size_t)STAGES * (MT * A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + 256 + 8 * BLOCK_N * 4 + 1024 + 64;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    const int total = (int)(grid.x * grid.y * grid.z);
+    const int total = (int)(((grid.x + MT - 1) / MT) * grid.y * grid.z);
     const int ctas = total < ipr_sm_count() ? total : ipr_sm_count();       // persistent: one CTA per SM
-    tapgemm_kernel<BLOCK_N, STAGES><<<ctas, NUM_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], mb, p);
+    tapgemm_kernel<BLOCK_N, STAGES, MT><<<ctas, NUM_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], mb, p);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -415,11 +437,16 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     }
     dim3 grid((unsigned)p.m_tiles, (unsigned)(d->n_total / d->block_n), (unsigned)d->n_phases);
     cudaStream_t st = ipr_cu(stream);
+    // Two M sub-tiles per CTA sharing one weight tile (25 % fewer bytes per flop) is implemented but OFF by default:
+    // on B200 it measured no faster (conv3 64->128 @16, batch 512: 590 vs 650 TFLOP/s; step 5.08 vs 5.02 ms) -- with
+    // the same 192 KB in flight the per-SM TMA throughput dropped from ~35 to ~24 B/clk.  IPR_TG_PAIR=1 enables it.
+    const long long single_tiles = (long long)grid.x * grid.y * grid.z;
+    const bool pair = single_tiles >= 3LL * ipr_sm_count() && getenv("IPR_TG_PAIR") != nullptr;
     switch (d->block_n) {
-        case 16:  return launch<16, 8>(ma, mb, p, grid, st);
-        case 32:  return launch<32, 8>(ma, mb, p, grid, st);
-        case 64:  return launch<64, 8>(ma, mb, p, grid, st);
-        case 128: return launch<128, 6>(ma, mb, p, grid, st);
-        default:  return launch<256, 4>(ma, mb, p, grid, st);
+        case 16:  return launch<16, 8, 1>(ma, mb, p, grid, st);
+        case 32:  return launch<32, 8, 1>(ma, mb, p, grid, st);
+        case 64:  return pair ? launch<64, 5, 2>(ma, mb, p, grid, st) : launch<64, 8, 1>(ma, mb, p, grid, st);
+        case 128: return pair ? launch<128, 4, 2>(ma, mb, p, grid, st) : launch<128, 6, 1>(ma, mb, p, grid, st);
+        default:  return launch<256, 4, 1>(ma, mb, p, grid, st);
     }
 }

@@ -36,6 +36,7 @@ struct WgParams {
     int8_t tap_dw[IPR_TG_MAX_PHASES][IPR_TG_MAX_TAPS];
     float *ws;
     int n_phases;
+    long long *dbg;       // optional per-CTA phase timestamps (profiling builds of the probe only)
 };
 
 struct Maps { CUtensorMap y[4]; CUtensorMap x[4]; };
@@ -54,6 +55,8 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
     constexpr uint32_t TMEM_COLS = 64 * X_UNITS < 32 ? 32 : 64 * X_UNITS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_begin = clock64();
+    const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     const int n_tiles = (p.n_units + X_UNITS - 1) / X_UNITS;
     const int m_blk = blockIdx.x / n_tiles, n_tile = blockIdx.x - m_blk * n_tiles;
     const int split = blockIdx.y, phase = blockIdx.z;
@@ -119,13 +122,16 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
                 umma_commit(bar_empty + 8 * s);
             }
             umma_commit(bar_tmem);
+            if (p.dbg) p.dbg[cta_lin * 8 + 1] = clock64() - t_begin;     // MMA issue loop finished
         }
         __syncwarp();
     } else {
         const int q = warp & 3;
         const int n = m_blk * 128 + q * 32 + lane;        // output channel (row of dW)
         float *dst_row = p.ws + (((size_t)split * p.n_phases + phase) * p.n_pad + n) * p.k_total;
+        if (p.dbg && warp == 2 && lane == 0) p.dbg[cta_lin * 8 + 0] = clock64() - t_begin;   // setup done
         if (num_kb > 0) { mbar_wait_backoff(bar_tmem, 0); tc_fence_after(); }
+        if (p.dbg && warp == 2 && lane == 0) p.dbg[cta_lin * 8 + 2] = clock64() - t_begin;   // accumulator ready
 #pragma unroll 1
         for (int c0 = 0; c0 < 64 * X_UNITS; c0 += 32) {
             const int unit = unit0 + (c0 >> 6);
@@ -145,6 +151,7 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
                                      __uint_as_float(raw[4 * g + 2]), __uint_as_float(raw[4 * g + 3]));
         }
     }
+    if (p.dbg && warp == 2 && lane == 0) { p.dbg[cta_lin * 8 + 3] = clock64() - t_begin; p.dbg[cta_lin * 8 + 4] = num_kb; }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -293,6 +300,7 @@ extern "C" int ipr_wgrad_bf16(const ipr_wgrad_t *d, ipr_stream_t stream)
     p.n_units = d->n_taps * p.x_chunks; p.n_phases = d->n_phases;
     p.kb_per_split = (p.total_kb + d->splits - 1) / d->splits;
     p.ws = d->workspace;
+    { const char *e = getenv("IPR_WGRAD_DBG_PTR"); p.dbg = e ? (long long *)strtoull(e, nullptr, 0) : nullptr; }
     for (int ph = 0; ph < IPR_TG_MAX_PHASES; ph++) {
         p.y_map[ph] = d->y_map[ph];
         for (int t = 0; t < IPR_TG_MAX_TAPS; t++) {
