@@ -52,7 +52,7 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
     const uint32_t bar_empty = bar_full + STAGES * 8;
     const uint32_t bar_tmem = bar_empty + STAGES * 8;
     const uint32_t tmem_slot = bar_tmem + 8;
-    constexpr uint32_t TMEM_COLS = 64 * X_UNITS < 32 ? 32 : 64 * X_UNITS;
+    constexpr uint32_t TMEM_COLS = X_UNITS <= 1 ? 64 : (X_UNITS == 2 ? 128 : 256);    // power of two >= 64 * X_UNITS
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t_begin = clock64();
@@ -204,7 +204,16 @@ int wgrad_config() {
     }
     return cfg;
 }
-int wgrad_x_units() { const int c = wgrad_config(); return c == 2 ? 4 : (c == 3 ? 1 : 2); }
+// X units per CTA tile: the widest of {4, 3, 2} that divides the layer's unit count (9-tap layers -> 3, 16-tap / 4-tap
+// layers -> 4): the kernel is paced by TMA requests per MAC, which fall by 25 % going from N = 128 to N = 192 / 256
+// (measured: 1027 -> 1248 cycles per k-block for twice the MACs), provided no tile is left partly empty.
+int wgrad_x_units(int n_units) {
+    const char *e = getenv("IPR_WGRAD_CFG");
+    if (e) { const int c = atoi(e); return c == 2 ? 4 : (c == 3 ? 1 : (c == 4 ? 3 : 2)); }
+    if (n_units % 4 == 0) return 4;
+    if (n_units % 3 == 0) return 3;
+    return 2;
+}
 
 template <int X_UNITS, int STAGES>
 int launch_wgrad(const Maps &maps, const WgParams &p, dim3 grid, cudaStream_t st)
@@ -316,14 +325,14 @@ extern "C" int ipr_wgrad_bf16(const ipr_wgrad_t *d, ipr_stream_t stream)
     rc = make_maps(d->x, d->x_c, xh, xw, d->n_imgs, d->x_parity, box, maps.x);
     if (rc) return rc;
 
-    const int xu = wgrad_x_units();
+    const int xu = wgrad_x_units(p.n_units);
     const int n_tiles = (p.n_units + xu - 1) / xu;
     dim3 grid((unsigned)((p.n_pad / 128) * n_tiles), (unsigned)d->splits, (unsigned)d->n_phases);
-    switch (wgrad_config()) {
-        case 0:  return launch_wgrad<2, 3>(maps, p, grid, ipr_cu(stream));
-        case 1:  return launch_wgrad<2, 6>(maps, p, grid, ipr_cu(stream));
-        case 2:  return launch_wgrad<4, 4>(maps, p, grid, ipr_cu(stream));
-        default: return launch_wgrad<1, 8>(maps, p, grid, ipr_cu(stream));
+    switch (xu) {
+        case 4:  return launch_wgrad<4, 4>(maps, p, grid, ipr_cu(stream));
+        case 3:  return launch_wgrad<3, 5>(maps, p, grid, ipr_cu(stream));
+        case 1:  return launch_wgrad<1, 8>(maps, p, grid, ipr_cu(stream));
+        default: return launch_wgrad<2, 6>(maps, p, grid, ipr_cu(stream));
     }
 }
 
@@ -331,7 +340,7 @@ extern "C" int ipr_wgrad_tiles(const ipr_wgrad_t *d)
 {
     if (!d) return IPR_E_NULL;
     const int n_units = d->n_taps * (d->x_c / 64);
-    const int xu = wgrad_x_units();
+    const int xu = wgrad_x_units(n_units);
     return ((d->y_c + 127) / 128) * ((n_units + xu - 1) / xu) * d->n_phases;
 }
 

@@ -160,13 +160,19 @@ class Plan(object):
         d.a, d.a_n, d.a_h, d.a_w, d.a_c = a.data_ptr(), N, H, W, C
         d.a_parity = self.a_parity
         d.q_h, d.q_w = (H // 2, W // 2) if self.a_parity else (H, W)
-        # tile width: the widest N tile that still yields about one tile per SM (wide tiles re-read A least, but a
-        # few wide tiles leave most of the chip idle and serialise a long K loop -- the small-batch regime)
-        block_n = self.block_n
+        # tile width: the kernel is paced by TMA row requests (128 A rows + BLOCK_N B rows per k-block and tile) and runs
+        # one persistent CTA per SM, so pick the N tile that minimises  waves(tiles / SMs) * (128 + BLOCK_N)
         m_pix = N * ((H // 2) * (W // 2) if self.a_parity else H * W)
         m_tiles = (m_pix + 127) // 128
-        while block_n > 64 and m_tiles * (self.n_total // block_n) * self.n_phases < _SM_COUNT_TILES:
-            block_n //= 2
+        block_n, best = self.block_n, None
+        bn = self.block_n
+        while bn >= 16:
+            if self.n_total % bn == 0:
+                tiles = m_tiles * (self.n_total // bn) * self.n_phases
+                cost = -(-tiles // _SM_COUNT) * (128 + bn) * (1.0 if bn >= 64 else 1.5)
+                if best is None or cost < best:
+                    best, block_n = cost, bn
+            bn //= 2
         d.b, d.n_total, d.block_n = b_packed.data_ptr(), self.n_total, block_n
         d.n_phases, d.n_taps = self.n_phases, self.n_taps
         for ph, taps in enumerate(self.taps):
@@ -295,8 +301,9 @@ class WGradPlan(object):
             check(kblocks, "ipr_wgrad_total_kblocks")
         if splits is None:
             tiles = L.ipr_wgrad_tiles(ctypes.byref(d))           # one CTA per SM (48 KB stages): fill the chip once
-            target = _SM_COUNT * _WGRAD_OVERSUB
-            splits = max(1, min(kblocks // 4 if kblocks >= 8 else 1, (target + tiles - 1) // tiles, 128))
+            # one CTA per SM (about 190 KB of smem stages): never exceed one wave, a second partial wave doubles the time
+            slots = _SM_COUNT * _WGRAD_OVERSUB
+            splits = max(1, min(kblocks // 4 if kblocks >= 8 else 1, slots // tiles, 128))
         d.splits = splits
         nbytes = L.ipr_wgrad_workspace_bytes(ctypes.byref(d))
         ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
