@@ -47,6 +47,7 @@ struct TgParams {
     int8_t out_oh[IPR_TG_MAX_PHASES], out_ow[IPR_TG_MAX_PHASES];
     int n_valid;
     float *stats;
+    long long *dbg;        // optional phase timestamps of CTA 0 (scripts/tile_phase_probe.py)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -54,7 +55,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-template <int BLOCK_N, int STAGES, int MT>
+template <int BLOCK_N, int STAGES, int MT, bool RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -75,15 +76,25 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-byte alignment
     const uint32_t sA = smem_base;
     const uint32_t sB = smem_base + STAGES * A_BYTES;
-    const uint32_t bar_full = sB + STAGES * B_STAGE_BYTES;                // STAGES x 8 bytes
+    // RES: the whole weight matrix of this layer (all taps, all phases; one N block) stays resident in shared memory
+    // for the lifetime of the persistent CTA, so only A tiles are streamed -- the kernel is paced by TMA row requests
+    // (128 A rows + BLOCK_N B rows per k-block), and high-resolution layers have small weights
+    const uint32_t b_region = RES ? (uint32_t)(p.n_phases * p.n_taps * p.c_chunks) * B_STAGE_BYTES
+                                  : (uint32_t)STAGES * B_STAGE_BYTES;
+    const uint32_t bar_full = sB + b_region;                               // STAGES x 8 bytes
     const uint32_t bar_empty = bar_full + STAGES * 8;
     const uint32_t bar_acc_full = bar_empty + STAGES * 8;                 // 2 x 8
     const uint32_t bar_acc_empty = bar_acc_full + 16;                     // 2 x 8
-    const uint32_t tmem_slot = bar_acc_empty + 16;
+    const uint32_t bar_bres = bar_acc_empty + 16;
+    const uint32_t tmem_slot = bar_bres + 8;
     // per-warp column statistics of the current tile: [warp 4][sum | sumsq][BLOCK_N] floats (epilogue warps only)
-    float *stat_sm = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + 256);   // after the mbarriers
+    float *stat_sm = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * A_BYTES + b_region + 256);   // after the mbarriers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.dbg && threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        p.dbg[64 + blockIdx.x * 2] = (long long)gt;
+    }
     const int num_kb = p.n_taps * p.c_chunks;
     const int n_blks = p.n_total / BLOCK_N;
     const int m_groups = (p.m_tiles + MT - 1) / MT;                 // CTA tiles along M
@@ -94,6 +105,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int b = 0; b < 2; b++) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, 4); }
+        mbar_init(bar_bres, 1);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -102,12 +114,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // everything above overlapped the previous kernel's tail (PDL); from here on its results are needed
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
 
     // persistent: CTA c processes tiles c, c + grid, c + 2 grid, ...   tile -> (phase, m_tile, n_blk), n_blk fastest
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t g = 0;                                            // running k-block counter across tiles
+            if (RES) {
+                mbar_expect_tx(bar_bres, b_region);
+                for (int ph = 0; ph < p.n_phases; ph++)
+                    for (int kb = 0; kb < num_kb; kb++)
+                        tma_load_2d(sB + (ph * num_kb + kb) * B_STAGE_BYTES, &mapB, bar_bres, kb * BLOCK_K, ph * p.n_total);
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int phase = tile / tiles_per_phase, rem = tile - phase * tiles_per_phase;
                 const int m_grp = rem / n_blks, n_blk = rem - m_grp * n_blks;
@@ -122,7 +143,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const int s = g % STAGES;
                     const uint32_t par = (g / STAGES) & 1u;
                     mbar_wait(bar_empty + 8 * s, par ^ 1u);
-                    mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+                    mbar_expect_tx(bar_full + 8 * s, RES ? A_BYTES : STAGE_BYTES);
                     const int tap = kb / p.c_chunks, cc = kb - tap * p.c_chunks;
                     const int mi = p.tap_map[phase][tap];
                     const CUtensorMap *ma = mi == 0 ? &mapA0 : (mi == 1 ? &mapA1 : (mi == 2 ? &mapA2 : &mapA3));
@@ -130,8 +151,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int j = 0; j < MT; j++)
                         tma_load_4d(sA + s * A_BYTES + j * A_STAGE_BYTES, ma, bar_full + 8 * s, cc * BLOCK_K,
                                     (int)p.tap_dw[phase][tap], h0[j] + (int)p.tap_dh[phase][tap], img0[j]);
-                    tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, bar_full + 8 * s, tap * p.a_c + cc * BLOCK_K,
-                                phase * p.n_total + n_blk * BLOCK_N);
+                    if (!RES)
+                        tma_load_2d(sB + s * B_STAGE_BYTES, &mapB, bar_full + 8 * s, tap * p.a_c + cc * BLOCK_K,
+                                    phase * p.n_total + n_blk * BLOCK_N);
                 }
             }
         }
@@ -141,9 +163,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
             uint32_t g = 0, it = 0;
+            if (RES) { mbar_wait(bar_bres, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+                const int phase_m = tile / tiles_per_phase;
                 const uint32_t buf = it & 1u;
+                if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 8 + 0] = clock64();
                 mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+                if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 8 + 1] = clock64();
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * BUF_COLS;
                 for (int kb = 0; kb < num_kb; kb++, g++) {
@@ -151,7 +177,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const uint32_t par = (g / STAGES) & 1u;
                     mbar_wait(bar_full + 8 * s, par);
                     tc_fence_after();
-                    const uint64_t db = umma_desc_sw128(sB + s * B_STAGE_BYTES, 0, 1024);
+                    const uint64_t db = umma_desc_sw128(RES ? sB + (phase_m * num_kb + kb) * B_STAGE_BYTES
+                                                            : sB + s * B_STAGE_BYTES, 0, 1024);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
 #pragma unroll
@@ -165,6 +192,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     umma_commit(bar_empty + 8 * s);           // smem stage reusable once these MMAs retire
                 }
                 umma_commit(bar_acc_full + 8 * buf);          // accumulator complete
+                if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 8 + 2] = clock64();
             }
         }
         __syncwarp();
@@ -181,8 +209,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int phase = tile / tiles_per_phase, rem = tile - phase * tiles_per_phase;
             const int m_grp = rem / n_blks, n_blk = rem - m_grp * n_blks;
             const uint32_t buf = it & 1u;
+            if (p.dbg && blockIdx.x == 0 && it < 8 && warp == 2 && lane == 0) p.dbg[it * 8 + 3] = clock64();
             mbar_wait_backoff(bar_acc_full + 8 * buf, (it >> 1) & 1u);
             tc_fence_after();
+            if (p.dbg && blockIdx.x == 0 && it < 8 && warp == 2 && lane == 0) p.dbg[it * 8 + 4] = clock64();
 #pragma unroll 1
           for (int sub = 0; sub < MT; sub++) {
             const int m_tile = m_grp * MT + sub;
@@ -311,28 +341,35 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
           }
+          if (p.dbg && blockIdx.x == 0 && it < 8 && warp == 2 && lane == 0) p.dbg[it * 8 + 5] = clock64();
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (p.dbg && threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        p.dbg[64 + blockIdx.x * 2 + 1] = (long long)gt;
+    }
 }
 
-template <int BLOCK_N, int STAGES, int MT>
+template <int BLOCK_N, int STAGES, int MT, bool RES>
 int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3 grid, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (MT * A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + 256 + 8 * BLOCK_N * 4 + 1024 + 64;
-    static_assert(smem <= 227 * 1024, "shared memory budget");
+    const size_t b_region = RES ? (size_t)p.n_phases * p.n_taps * p.c_chunks * BLOCK_N * BLOCK_K * 2
+                                : (size_t)STAGES * BLOCK_N * BLOCK_K * 2;
+    const size_t smem = (size_t)STAGES * MT * A_STAGE_BYTES + b_region + 256 + 8 * BLOCK_N * 4 + 1024 + 64;
+    if (smem > 227 * 1024) return IPR_E_UNSUPPORTED;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES, MT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
     const int total = (int)(((grid.x + MT - 1) / MT) * grid.y * grid.z);
     const int ctas = total < ipr_sm_count() ? total : ipr_sm_count();       // persistent: one CTA per SM
-    tapgemm_kernel<BLOCK_N, STAGES, MT><<<ctas, NUM_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], mb, p);
+    IPR_LAUNCH_PDL((tapgemm_kernel<BLOCK_N, STAGES, MT, RES>), ctas, NUM_THREADS, smem, st, ma[0], ma[1], ma[2], ma[3], mb, p);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -404,6 +441,7 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     p.mask = (const __nv_bfloat16 *)d->mask; p.out = d->out;
     p.out_h = d->out_h; p.out_w = d->out_w; p.out_c = d->out_c; p.out_sh = d->out_sh; p.out_sw = d->out_sw;
     p.n_valid = d->n_valid > 0 ? d->n_valid : d->n_total; p.stats = d->stats;
+    { const char *e = getenv("IPR_TG_DBG_PTR"); p.dbg = e ? (long long *)strtoull(e, nullptr, 0) : nullptr; }
 
     // ---- tensor maps (host-encoded, passed by value as kernel parameters: graph-capturable)
     CUtensorMap ma[4], mb;
@@ -442,11 +480,25 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     // the same 192 KB in flight the per-SM TMA throughput dropped from ~35 to ~24 B/clk.  IPR_TG_PAIR=1 enables it.
     const long long single_tiles = (long long)grid.x * grid.y * grid.z;
     const bool pair = single_tiles >= 3LL * ipr_sm_count() && getenv("IPR_TG_PAIR") != nullptr;
+    // weights resident in shared memory: one N block, everything (all phases x taps) fits beside 4 A stages, and every
+    // CTA has at least two tiles to amortise the one-off weight load over
+    const size_t b_all = (size_t)d->n_phases * d->n_taps * p.c_chunks * d->block_n * BLOCK_K * 2;
+    const bool resident = d->n_total == d->block_n && b_all <= 150 * 1024 && single_tiles >= 2LL * ipr_sm_count() &&
+                          getenv("IPR_TG_NO_RESIDENT") == nullptr;
+    if (resident) {
+        switch (d->block_n) {
+            case 16:  return launch<16, 4, 1, true>(ma, mb, p, grid, st);
+            case 32:  return launch<32, 4, 1, true>(ma, mb, p, grid, st);
+            case 64:  return launch<64, 4, 1, true>(ma, mb, p, grid, st);
+            case 128: return launch<128, 4, 1, true>(ma, mb, p, grid, st);
+            default:  break;
+        }
+    }
     switch (d->block_n) {
-        case 16:  return launch<16, 8, 1>(ma, mb, p, grid, st);
-        case 32:  return launch<32, 8, 1>(ma, mb, p, grid, st);
-        case 64:  return pair ? launch<64, 5, 2>(ma, mb, p, grid, st) : launch<64, 8, 1>(ma, mb, p, grid, st);
-        case 128: return pair ? launch<128, 4, 2>(ma, mb, p, grid, st) : launch<128, 6, 1>(ma, mb, p, grid, st);
-        default:  return launch<256, 4, 1>(ma, mb, p, grid, st);
+        case 16:  return launch<16, 8, 1, false>(ma, mb, p, grid, st);
+        case 32:  return launch<32, 8, 1, false>(ma, mb, p, grid, st);
+        case 64:  return pair ? launch<64, 5, 2, false>(ma, mb, p, grid, st) : launch<64, 8, 1, false>(ma, mb, p, grid, st);
+        case 128: return pair ? launch<128, 4, 2, false>(ma, mb, p, grid, st) : launch<128, 6, 1, false>(ma, mb, p, grid, st);
+        default:  return launch<256, 4, 1, false>(ma, mb, p, grid, st);
     }
 }

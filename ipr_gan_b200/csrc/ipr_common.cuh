@@ -71,3 +71,32 @@ __device__ __forceinline__ void ipr_stg_stream4(float4 *p, const float4 &v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel of the step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs may become resident and run their
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, index math) while the previous kernel drains; each
+// kernel calls ipr_pdl_wait() before it touches global memory (full completion + visibility of the predecessor) and
+// then ipr_pdl_trigger() so its own successor can start early.  Inside the captured CUDA graph this turns the ~250
+// kernel-to-kernel launch gaps of a step into overlapped prologues.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ipr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ipr_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ipr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define IPR_LAUNCH_PDL(kernel, grid, block, smem, st, ...)                                         \
+    do {                                                                                           \
+        cudaError_t e__ = ipr_launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__); \
+        if (e__ != cudaSuccess) return (int)e__;                                                   \
+    } while (0)

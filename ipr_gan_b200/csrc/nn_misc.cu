@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(256)
 im2col3_kernel(const float *__restrict__ x, const float *__restrict__ t, uint4 *__restrict__ out,
                long long pixels, int H, int W)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const size_t plane = (size_t)H * W;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += stride) {
@@ -87,6 +89,8 @@ bn_finalize_kernel(const float *__restrict__ partial, int rows, int C, double co
                    float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ mean_out,
                    float *__restrict__ rstd_out)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ double s1[8][33], s2[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     double a = 0.0, b = 0.0;
@@ -122,6 +126,8 @@ __global__ void __launch_bounds__(256)
 bn_apply_relu_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, const float *__restrict__ scale,
                      const float *__restrict__ shift, long long n_vec, int c_vec)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
         const int c0 = (int)(i % c_vec) * 8;
@@ -140,6 +146,8 @@ bn_bwd_reduce_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xra
                      const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
                      long long rows, int c_vec, float *__restrict__ partial)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     extern __shared__ float sm[];                    // [ry][2][C]
     const int C = c_vec * 8;
     const int ry_n = blockDim.x / c_vec;
@@ -186,6 +194,8 @@ bn_bwd_finalize_kernel(const float *__restrict__ partial, int rows, int C, doubl
                        const float *__restrict__ sign, float gamma0, float sign_scale,
                        float *__restrict__ coef)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ double s1[32][33], s2[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -217,6 +227,8 @@ bn_bwd_apply_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xraw
                     const float *__restrict__ shift, const float *__restrict__ coef, uint4 *__restrict__ dx,
                     long long n_vec, int c_vec)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const int C = c_vec * 8;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
@@ -239,6 +251,8 @@ __global__ void __launch_bounds__(256)
 dfc_fwd_kernel(const uint4 *__restrict__ a, const float *__restrict__ w, const float *__restrict__ sigma,
                const float *__restrict__ bias, float *__restrict__ logits, int batch, int k_vec)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float red[32];
     const int b = blockIdx.x;
     float acc = 0.0f;
@@ -257,6 +271,8 @@ __global__ void __launch_bounds__(256)
 dfc_bwd_data_kernel(const uint4 *__restrict__ a, const float *__restrict__ w, const float *__restrict__ sigma,
                     const float *__restrict__ dlogit, uint4 *__restrict__ da, long long n_vec, int k_vec, float slope)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const float inv = 1.0f / (sigma ? *sigma : 1.0f);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
@@ -278,6 +294,8 @@ __global__ void __launch_bounds__(256)
 dfc_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ dlogit, float *__restrict__ dw,
                       int batch, int K, int accumulate)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int k = blockIdx.x * 32 + tx;
@@ -309,7 +327,7 @@ extern "C" int ipr_im2col3_bf16(const float *x, const float *tanh_out, void *out
     IPR_REQUIRE(batch > 0 && height > 0 && width > 0, IPR_E_SHAPE);
     IPR_REQUIRE(ipr_aligned16(out), IPR_E_ALIGN);
     const long long pixels = (long long)batch * height * width;
-    im2col3_kernel<<<grid_1d(pixels, 256), 256, 0, ipr_cu(stream)>>>(x, tanh_out, (uint4 *)out, pixels, height, width);
+    IPR_LAUNCH_PDL((im2col3_kernel), grid_1d(pixels, 256), 256, 0, ipr_cu(stream), x, tanh_out, (uint4 *)out, pixels, height, width);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -322,7 +340,7 @@ extern "C" int ipr_bn_finalize_f32(const float *partial, int rows, int channels,
     IPR_REQUIRE(partial && gamma && beta && scale && shift && mean && rstd, IPR_E_NULL);
     IPR_REQUIRE(rows > 0 && channels > 0 && count > 0, IPR_E_SHAPE);
     dim3 block(32, 8);
-    bn_finalize_kernel<<<(channels + 31) / 32, block, 0, ipr_cu(stream)>>>(
+    IPR_LAUNCH_PDL((bn_finalize_kernel), (channels + 31) / 32, block, 0, ipr_cu(stream), 
         partial, rows, channels, count, eps, momentum, gamma, beta, running_mean, running_var,
         (long long *)num_batches_tracked, scale, shift, mean, rstd);
     IPR_LAUNCH_CHECK();
@@ -336,7 +354,7 @@ extern "C" int ipr_bn_apply_relu_bf16(const void *x, void *y, const float *scale
     IPR_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0, IPR_E_SHAPE);
     IPR_REQUIRE(ipr_aligned16(x) && ipr_aligned16(y), IPR_E_ALIGN);
     const long long n_vec = (long long)rows * channels / 8;
-    bn_apply_relu_kernel<<<grid_1d(n_vec, 256), 256, 0, ipr_cu(stream)>>>((const uint4 *)x, (uint4 *)y, scale, shift,
+    IPR_LAUNCH_PDL((bn_apply_relu_kernel), grid_1d(n_vec, 256), 256, 0, ipr_cu(stream), (const uint4 *)x, (uint4 *)y, scale, shift,
                                                                         n_vec, channels / 8);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
@@ -375,15 +393,15 @@ extern "C" int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const floa
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    bn_bwd_reduce_kernel<<<(unsigned)ctas, 256, smem, st>>>((const uint4 *)dy, (const uint4 *)xraw, scale, shift,
+    IPR_LAUNCH_PDL((bn_bwd_reduce_kernel), (unsigned)ctas, 256, smem, st, (const uint4 *)dy, (const uint4 *)xraw, scale, shift,
                                                             mean, rstd, rows, c_vec, partial);
     IPR_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<(channels + 31) / 32, 1024, 0, st>>>(partial, (int)ctas, channels, (double)rows, gamma, mean,
+    IPR_LAUNCH_PDL((bn_bwd_finalize_kernel), (channels + 31) / 32, 1024, 0, st, partial, (int)ctas, channels, (double)rows, gamma, mean,
                                                                   rstd, dgamma, dbeta, accumulate, sign, gamma0,
                                                                   sign_scale, coef);
     IPR_LAUNCH_CHECK();
     const long long n_vec = (long long)rows * c_vec;
-    bn_bwd_apply_kernel<<<grid_1d(n_vec, 256), 256, 0, st>>>((const uint4 *)dy, (const uint4 *)xraw, scale, shift,
+    IPR_LAUNCH_PDL((bn_bwd_apply_kernel), grid_1d(n_vec, 256), 256, 0, st, (const uint4 *)dy, (const uint4 *)xraw, scale, shift,
                                                              coef, (uint4 *)dx, n_vec, c_vec);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
@@ -395,7 +413,7 @@ extern "C" int ipr_dfc_fwd_bf16(const void *a, const float *w, const float *sigm
     IPR_REQUIRE(a && w && logits, IPR_E_NULL);
     IPR_REQUIRE(batch > 0 && k > 0 && k % 8 == 0, IPR_E_SHAPE);
     IPR_REQUIRE(ipr_aligned16(a) && ipr_aligned16(w), IPR_E_ALIGN);
-    dfc_fwd_kernel<<<batch, 256, 0, ipr_cu(stream)>>>((const uint4 *)a, w, sigma, bias, logits, batch, k / 8);
+    IPR_LAUNCH_PDL((dfc_fwd_kernel), batch, 256, 0, ipr_cu(stream), (const uint4 *)a, w, sigma, bias, logits, batch, k / 8);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -408,11 +426,11 @@ extern "C" int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigm
     IPR_REQUIRE(batch > 0 && k > 0 && k % 8 == 0, IPR_E_SHAPE);
     IPR_REQUIRE(ipr_aligned16(a) && ipr_aligned16(w) && ipr_aligned16(da), IPR_E_ALIGN);
     const long long n_vec = (long long)batch * k / 8;
-    dfc_bwd_data_kernel<<<grid_1d(n_vec, 256), 256, 0, ipr_cu(stream)>>>((const uint4 *)a, w, sigma, dlogit, (uint4 *)da,
+    IPR_LAUNCH_PDL((dfc_bwd_data_kernel), grid_1d(n_vec, 256), 256, 0, ipr_cu(stream), (const uint4 *)a, w, sigma, dlogit, (uint4 *)da,
                                                                         n_vec, k / 8, slope);
     IPR_LAUNCH_CHECK();
     if (dw) {
-        dfc_bwd_weight_kernel<<<(k + 31) / 32, 256, 0, ipr_cu(stream)>>>((const __nv_bfloat16 *)a, dlogit, dw, batch, k,
+        IPR_LAUNCH_PDL((dfc_bwd_weight_kernel), (k + 31) / 32, 256, 0, ipr_cu(stream), (const __nv_bfloat16 *)a, dlogit, dw, batch, k,
                                                                          accumulate_dw);
         IPR_LAUNCH_CHECK();
     }
@@ -427,6 +445,8 @@ namespace {
 __global__ void __launch_bounds__(256)
 colsum_partials_stage1(const float *__restrict__ in, int rows, int ncols, int row_stride, float *__restrict__ out)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -446,6 +466,8 @@ __global__ void __launch_bounds__(256)
 colsum_small_kernel(const float *__restrict__ in, int rows, int ncols, int row_stride, float *__restrict__ out,
                     int accumulate, float scale)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -464,6 +486,8 @@ colsum_small_kernel(const float *__restrict__ in, int rows, int ncols, int row_s
 __global__ void __launch_bounds__(256)
 colsum_stage2(const float *__restrict__ in, int rows, int ncols, float *__restrict__ out, int accumulate, float scale)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncols) return;
     double acc = 0.0;
@@ -475,6 +499,8 @@ colsum_stage2(const float *__restrict__ in, int rows, int ncols, float *__restri
 __global__ void __launch_bounds__(256)
 colsum_bf16_stage1(const uint4 *__restrict__ x, long long rows, int c_vec, float *__restrict__ out)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     // grid.x = column groups of 256 vectors, grid.y = row slabs
     const int cv = blockIdx.x * blockDim.x + threadIdx.x;
     if (cv >= c_vec) return;
@@ -505,15 +531,15 @@ extern "C" int ipr_colsum_partials_f32(const float *partial, int rows, int ncols
     IPR_REQUIRE(rows > 0 && ncols > 0, IPR_E_SHAPE);
     IPR_REQUIRE(workspace_bytes >= ipr_colsum_workspace_bytes(ncols), IPR_E_WORKSPACE);
     if (rows <= 256) {                      // few rows: one launch, every CTA reduces its 32 columns completely
-        colsum_small_kernel<<<(ncols + 31) / 32, 256, 0, ipr_cu(stream)>>>(partial, rows, ncols, row_stride, out, accumulate, scale);
+        IPR_LAUNCH_PDL((colsum_small_kernel), (ncols + 31) / 32, 256, 0, ipr_cu(stream), partial, rows, ncols, row_stride, out, accumulate, scale);
         IPR_LAUNCH_CHECK();
         return IPR_OK;
     }
     const int G = rows < 8 * 64 ? (rows + 7) / 8 : 64;
     dim3 grid((ncols + 31) / 32, G);
-    colsum_partials_stage1<<<grid, 256, 0, ipr_cu(stream)>>>(partial, rows, ncols, row_stride, (float *)workspace);
+    IPR_LAUNCH_PDL((colsum_partials_stage1), grid, 256, 0, ipr_cu(stream), partial, rows, ncols, row_stride, (float *)workspace);
     IPR_LAUNCH_CHECK();
-    colsum_stage2<<<(ncols + 255) / 256, 256, 0, ipr_cu(stream)>>>((const float *)workspace, G, ncols, out, accumulate, scale);
+    IPR_LAUNCH_PDL((colsum_stage2), (ncols + 255) / 256, 256, 0, ipr_cu(stream), (const float *)workspace, G, ncols, out, accumulate, scale);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -529,9 +555,9 @@ extern "C" int ipr_colsum_bf16(const void *x, int64_t rows, int channels, float 
     const int G = rows < 64 ? (int)rows : 64;
     dim3 grid((c_vec + 255) / 256, G);
     const int threads = c_vec < 256 ? ((c_vec + 31) / 32) * 32 : 256;
-    colsum_bf16_stage1<<<grid, threads, 0, ipr_cu(stream)>>>((const uint4 *)x, rows, c_vec, (float *)workspace);
+    IPR_LAUNCH_PDL((colsum_bf16_stage1), grid, threads, 0, ipr_cu(stream), (const uint4 *)x, rows, c_vec, (float *)workspace);
     IPR_LAUNCH_CHECK();
-    colsum_stage2<<<(channels + 255) / 256, 256, 0, ipr_cu(stream)>>>((const float *)workspace, G, channels, out,
+    IPR_LAUNCH_PDL((colsum_stage2), (channels + 255) / 256, 256, 0, ipr_cu(stream), (const float *)workspace, G, channels, out,
                                                                     accumulate, scale);
     IPR_LAUNCH_CHECK();
     return IPR_OK;

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256)
 adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                  long long n, float lr, float b1, float b2, float eps, float wd, const float *__restrict__ step)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const float t = *step + 1.0f;
     const float bc1 = 1.0f - powf(b1, t);
     const float bc2_sqrt = sqrtf(1.0f - powf(b2, t));
@@ -43,11 +45,18 @@ adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
     }
 }
 
-__global__ void step_increment_kernel(float *step) { *step += 1.0f; }
+__global__ void step_increment_kernel(float *step)
+{
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
+    *step += 1.0f;
+}
 
 __global__ void __launch_bounds__(256)
 gather_pack_kernel(const float *__restrict__ src, const int *__restrict__ idx, __nv_bfloat16 *__restrict__ dst, long long n)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long n8 = n >> 3;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
@@ -81,10 +90,10 @@ extern "C" int ipr_adam_flat_f32(float *param, const float *grad, float *exp_avg
     const long long cap = (long long)ipr_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_flat_kernel<<<(unsigned)blocks, 256, 0, ipr_cu(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+    IPR_LAUNCH_PDL((adam_flat_kernel), (unsigned)blocks, 256, 0, ipr_cu(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                   eps, weight_decay, step);
     IPR_LAUNCH_CHECK();
-    step_increment_kernel<<<1, 1, 0, ipr_cu(stream)>>>(step);
+    IPR_LAUNCH_PDL((step_increment_kernel), 1, 1, 0, ipr_cu(stream), step);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -97,7 +106,7 @@ extern "C" int ipr_gather_pack_bf16(const float *src, const int32_t *index, void
     long long blocks = (n / 8 + 255) / 256;
     const long long cap = (long long)ipr_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    gather_pack_kernel<<<(unsigned)blocks, 256, 0, ipr_cu(stream)>>>(src, index, (__nv_bfloat16 *)dst, n);
+    IPR_LAUNCH_PDL((gather_pack_kernel), (unsigned)blocks, 256, 0, ipr_cu(stream), src, index, (__nv_bfloat16 *)dst, n);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(512)
 sign_loss_kernel(const __grid_constant__ SignTable tab, float gamma0, float grad_scale, int accumulate,
                  float *__restrict__ loss)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float red[32];
     float total = 0.0f;
     for (int l = 0; l < tab.n_layers; l++) {
@@ -84,7 +86,7 @@ extern "C" int ipr_sign_loss_fwd_bwd_f32(const ipr_sign_layer_t *layers_host, in
     int rc = fill_table(t, layers_host, n_layers);
     if (rc != IPR_OK) return rc;
     IPR_REQUIRE(loss, IPR_E_NULL);
-    sign_loss_kernel<<<1, 512, 0, ipr_cu(stream)>>>(t, gamma0, grad_scale, accumulate, loss);
+    IPR_LAUNCH_PDL((sign_loss_kernel), 1, 512, 0, ipr_cu(stream), t, gamma0, grad_scale, accumulate, loss);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

@@ -26,6 +26,8 @@ constexpr int ROW_CHUNK = 32;
 __global__ void __launch_bounds__(256)
 sn_wtu_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const int l = find_layer(tab, blockIdx.x);
     const ipr_sn_layer_t L = tab.layer[l];
     const int local = blockIdx.x - tab.cta_begin[l];
@@ -44,6 +46,8 @@ sn_wtu_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
 __global__ void __launch_bounds__(1024)
 sn_v_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scratch, float eps)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float red[32];
     const ipr_sn_layer_t L = tab.layer[blockIdx.x];
     const int chunks = (L.rows + ROW_CHUNK - 1) / ROW_CHUNK;
@@ -63,6 +67,8 @@ sn_v_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scrat
 __global__ void __launch_bounds__(256)
 sn_wv_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float red[32];
     const int l = find_layer(tab, blockIdx.x);
     const ipr_sn_layer_t L = tab.layer[l];
@@ -86,6 +92,8 @@ sn_wv_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
 __global__ void __launch_bounds__(1024)
 sn_u_sigma_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scratch, float eps, int update)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float red[32];
     const ipr_sn_layer_t L = tab.layer[blockIdx.x];
     float acc = 0.0f;
@@ -110,6 +118,8 @@ constexpr int DOT_SPAN = 256 * 16;
 __global__ void __launch_bounds__(256)
 sn_dot_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float red[32];
     const int l = find_layer(tab, blockIdx.x);
     const ipr_sn_layer_t L = tab.layer[l];
@@ -139,6 +149,8 @@ sn_dot_kernel(const __grid_constant__ SnTable tab, float *__restrict__ scratch)
 __global__ void __launch_bounds__(256)
 sn_grad_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scratch)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float red[32];
     const int l = find_layer(tab, blockIdx.x);
     const ipr_sn_layer_t L = tab.layer[l];
@@ -198,17 +210,17 @@ extern "C" int ipr_sn_power_iter_f32(const ipr_sn_layer_t *layers_host, int n_la
             total += ((t.layer[i].rows + ROW_CHUNK - 1) / ROW_CHUNK) * ((t.layer[i].cols + 255) / 256);
         }
         t.cta_begin[n_layers] = total;
-        sn_wtu_kernel<<<total, 256, 0, st>>>(t, scratch);
+        IPR_LAUNCH_PDL((sn_wtu_kernel), total, 256, 0, st, t, scratch);
         IPR_LAUNCH_CHECK();
-        sn_v_kernel<<<n_layers, 1024, 0, st>>>(t, scratch, eps);
+        IPR_LAUNCH_PDL((sn_v_kernel), n_layers, 1024, 0, st, t, scratch, eps);
         IPR_LAUNCH_CHECK();
     }
     int total = 0;
     for (int i = 0; i < n_layers; i++) { t.cta_begin[i] = total; total += t.layer[i].rows; }
     t.cta_begin[n_layers] = total;
-    sn_wv_kernel<<<total, 256, 0, st>>>(t, scratch);
+    IPR_LAUNCH_PDL((sn_wv_kernel), total, 256, 0, st, t, scratch);
     IPR_LAUNCH_CHECK();
-    sn_u_sigma_kernel<<<n_layers, 1024, 0, st>>>(t, scratch, eps, update);
+    IPR_LAUNCH_PDL((sn_u_sigma_kernel), n_layers, 1024, 0, st, t, scratch, eps, update);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -228,9 +240,9 @@ extern "C" int ipr_sn_weight_grad_f32(const ipr_sn_layer_t *layers_host, int n_l
         total += (int)(((long long)t.layer[i].rows * t.layer[i].cols + DOT_SPAN - 1) / DOT_SPAN);
     }
     t.cta_begin[n_layers] = total;
-    sn_dot_kernel<<<total, 256, 0, st>>>(t, scratch);
+    IPR_LAUNCH_PDL((sn_dot_kernel), total, 256, 0, st, t, scratch);
     IPR_LAUNCH_CHECK();
-    sn_grad_kernel<<<total, 256, 0, st>>>(t, scratch);
+    IPR_LAUNCH_PDL((sn_grad_kernel), total, 256, 0, st, t, scratch);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

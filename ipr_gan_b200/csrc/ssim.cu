@@ -343,6 +343,8 @@ template <bool WITH_GRAD>
 __global__ void __launch_bounds__(128)
 ssim32_warp_kernel(const SsimParams p)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *base = smem + warp * S32_WARP_FLOATS;
@@ -482,6 +484,8 @@ ssim32_warp_kernel(const SsimParams p)
 __global__ void __launch_bounds__(1024)
 ssim_finalize_loss_kernel(const float *__restrict__ partial, long long n, float inv_count, float *__restrict__ loss)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     __shared__ float red[32];
     float acc = 0.f;
     for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
@@ -560,7 +564,7 @@ int launch_warp32(const SsimParams &p, cudaStream_t st)
     long long ctas = (p.planes + WARPS - 1) / WARPS;
     const long long cap = (long long)ipr_sm_count() * 2;          // 2 CTAs (8 warps) per SM, persistent over planes
     if (ctas > cap) ctas = cap;
-    ssim32_warp_kernel<WITH_GRAD><<<(unsigned)ctas, WARPS * 32, smem, st>>>(p);
+    IPR_LAUNCH_PDL((ssim32_warp_kernel<WITH_GRAD>), (unsigned)ctas, WARPS * 32, smem, st, p);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -618,7 +622,7 @@ extern "C" int ipr_ssim_fwd_bwd_f32(const float *x, const float *y, float *dx, f
     rc = dx ? launch_tiles<true>(p, pl, ipr_cu(stream)) : launch_tiles<false>(p, pl, ipr_cu(stream));
     if (rc != IPR_OK) return rc;
     const long long n = p.planes * pl.tiles_r * pl.tiles_c;
-    ssim_finalize_loss_kernel<<<1, 1024, 0, ipr_cu(stream)>>>(p.partial, n, (float)(1.0 / count), loss);
+    IPR_LAUNCH_PDL((ssim_finalize_loss_kernel), 1, 1024, 0, ipr_cu(stream), p.partial, n, (float)(1.0 / count), loss);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

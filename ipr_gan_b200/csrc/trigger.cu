@@ -32,6 +32,8 @@ paste_vec4_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, const fl
                   const float *__restrict__ bg, long long n_vec, PasteGeom g,
                   const float4 *__restrict__ z, float4 *__restrict__ xwm, long long z_vec)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int w4 = g.W >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
@@ -122,6 +124,8 @@ bitmask_kernel(const float *__restrict__ z, float *__restrict__ out, const long 
 __global__ void __launch_bounds__(256)
 tdist_kernel(const float *__restrict__ z, float *__restrict__ out, long long n)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = tdist_one(z[i]);
@@ -160,7 +164,7 @@ int paste_impl(const float *x, float *y, const float *fg, const float *bg, int64
     const bool vec = (W % 4 == 0) && ipr_aligned16(x) && ipr_aligned16(y) &&
                      (zn == 0 || (zn % 4 == 0 && ipr_aligned16(z) && ipr_aligned16(xwm)));
     if (vec) {
-        paste_vec4_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(
+        IPR_LAUNCH_PDL((paste_vec4_kernel), grid_for(n / 4, 256), 256, 0, st, 
             (const float4 *)x, (float4 *)y, fg, bg, n / 4, g, (const float4 *)z, (float4 *)xwm, zn / 4);
     } else {
         paste_scalar_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, fg, bg, n, g, z, xwm, zn);
@@ -219,7 +223,7 @@ extern "C" int ipr_transform_dist_f32(const float *z, float *out, int64_t numel,
 {
     IPR_REQUIRE(z && out, IPR_E_NULL);
     IPR_REQUIRE(numel > 0, IPR_E_SHAPE);
-    tdist_kernel<<<grid_for(numel, 256), 256, 0, ipr_cu(stream)>>>(z, out, numel);
+    IPR_LAUNCH_PDL((tdist_kernel), grid_for(numel, 256), 256, 0, ipr_cu(stream), z, out, numel);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

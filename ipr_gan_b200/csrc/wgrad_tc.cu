@@ -77,6 +77,8 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    ipr_pdl_wait();                 // prologue above overlapped the previous kernel's tail (PDL)
+    ipr_pdl_trigger();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -165,6 +167,8 @@ wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int phases, int n_
                     const int *__restrict__ dst_off, const int *__restrict__ row_map, long long s_n,
                     float *__restrict__ grad, int accumulate, float scale)
 {
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
     const long long total = (long long)phases * n_rows * k_total;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -225,7 +229,7 @@ int launch_wgrad(const Maps &maps, const WgParams &p, dim3 grid, cudaStream_t st
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    wgrad_kernel<X_UNITS, STAGES><<<grid, NUM_THREADS, smem, st>>>(maps, p);
+    IPR_LAUNCH_PDL((wgrad_kernel<X_UNITS, STAGES>), grid, NUM_THREADS, smem, st, maps, p);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -352,7 +356,7 @@ extern "C" int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phas
     IPR_REQUIRE(splits > 0 && phases > 0 && n_rows > 0 && k_total > 0, IPR_E_SHAPE);
     const int n_pad = ((n_rows + 127) / 128) * 128;
     const long long total = (long long)phases * n_rows * k_total;
-    wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ipr_cu(stream)>>>(workspace, splits, phases, n_rows, n_pad,
+    IPR_LAUNCH_PDL((wgrad_reduce_kernel), (unsigned)((total + 255) / 256), 256, 0, ipr_cu(stream), workspace, splits, phases, n_rows, n_pad,
                                                                                    k_total, dst_off, row_map,
                                                                                    (long long)s_n, grad, accumulate, scale);
     IPR_LAUNCH_CHECK();
