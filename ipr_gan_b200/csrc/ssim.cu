@@ -332,148 +332,244 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return d;
 }
 
-constexpr int S32_P_PITCH = 33;                  // float2 per row of the (x,y) plane
-constexpr int S32_D_PITCH = 23;                  // elements per row of the 22-wide maps
-constexpr int S32_WARP_FLOATS = 2 * 32 * S32_D_PITCH + 32 * S32_D_PITCH      // region A: P (2*32*33) or E (pq + r)
-                                + 2 * 2 * 22 * S32_P_PITCH                   // region B: Va, Vb
-                                + 2 * 22 * S32_D_PITCH + 22 * S32_D_PITCH + 6; // region C: Dpq, Dr
-static_assert(2 * 32 * S32_D_PITCH + 32 * S32_D_PITCH >= 2 * 32 * S32_P_PITCH, "E must cover P");
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));      // <= 1 ulp; the map denominators are >= C1*C2 > 0
+    return r;
+}
 
-template <bool WITH_GRAD>
-__global__ void __launch_bounds__(128)
+// Per-warp shared-memory carve (bytes).  Every array is indexed [line][lane] or [lane][line], so the aliases below are
+// same-lane aliases only (no cross-lane hazard beyond the __syncwarp between passes):
+//   P   float2 [32][33]  @0       (x, y) pairs; alive for the whole plane (pass 4 reads x, y from it and parks dX in .x)
+//   V   float2 [22][33]  @8448    vertically filtered pairs, written twice (means, then second moments)
+//   M   rows of 264 B    @8448    row r = { r-map[22] float @0, (p,q)-maps[22] float2 @88 }: rows 0..21 first hold
+//                                 D = dS/d(p,q,r) (row r overlays V row r, written behind the read position of the lane
+//                                 that owns that row), then all 32 rows hold E = G^T * D (row r overlays D row r).
+constexpr int S32_PF = 4;                        // shared-memory loads run this many lines ahead of the stores
+constexpr int S32_PITCH = 33;                    // float2 per row of P and V
+constexpr int S32_OFF_M = 32 * S32_PITCH * 8;    // 8448
+constexpr int S32_ROW_M = 22 * 4 + 22 * 8;       // 264 = one V row
+constexpr int S32_WARP_BYTES = S32_OFF_M + 32 * S32_ROW_M;           // 16896 -> 12 warps per SM
+static_assert(S32_ROW_M == S32_PITCH * 8, "a D/E row overlays exactly one V row");
+static_assert(S32_PF >= 1, "pass 2b stores D(p,q)[j] over V[j+11], which must already be in registers");
+static_assert(S32_WARP_BYTES % 16 == 0, "warp regions stay 16-byte aligned");
+
+template <bool WITH_GRAD, bool NORM>
+__global__ void __launch_bounds__(128, 3)
 ssim32_warp_kernel(const SsimParams p)
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *base = smem + warp * S32_WARP_FLOATS;
-    float2 *P = reinterpret_cast<float2 *>(base);                                 // [32][33]  (x, y)
-    float2 *Epq = reinterpret_cast<float2 *>(base);                               // [32][23]  aliases P (dead after pass 1)
-    float *Er = base + 2 * 32 * S32_D_PITCH;                                      // [32][23]
-    float2 *Va = reinterpret_cast<float2 *>(base + 2 * 32 * S32_D_PITCH + 32 * S32_D_PITCH + ((32 * S32_D_PITCH) & 1));
-    float2 *Vb = Va + 22 * S32_P_PITCH;                                           // [22][33] each
-    float2 *Dpq = Vb + 22 * S32_P_PITCH;                                          // [22][23]
-    float *Dr = reinterpret_cast<float *>(Dpq + 22 * S32_D_PITCH);                // [22][23]
+    unsigned char *base = smem_raw + warp * S32_WARP_BYTES;
+    float2 *P = reinterpret_cast<float2 *>(base);
+    float2 *V = reinterpret_cast<float2 *>(base + S32_OFF_M);
+    auto Mr = [&](int row) { return reinterpret_cast<float *>(base + S32_OFF_M + row * S32_ROW_M); };
+    auto Mpq = [&](int row) { return reinterpret_cast<float2 *>(base + S32_OFF_M + row * S32_ROW_M + 88); };
     const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
     float2 g2[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) g2[k] = make_float2(kTap[k], kTap[k]);
     auto tap2 = [&](int k) { return g2[k <= 5 ? k : 10 - k]; };
+    const int l22 = lane < 22 ? lane : 21;       // lanes 22..31 shadow line 21 in the 22-line passes (stores masked)
+    const bool act = lane < 22;
 
     for (long long plane = (long long)blockIdx.x * (blockDim.x >> 5) + warp; plane < p.planes; plane += warps_total) {
         const float *xg = p.x + plane * 1024, *yg = p.y + plane * 1024;
-        // ---- phase 0: 8 + 8 coalesced 128-bit loads per lane, interleave into (x, y) pairs
+        if (plane + warps_total < p.planes) {                  // pull this warp's next plane into L2 (one 128-B line per lane)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(xg + warps_total * 1024 + lane * 32));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(yg + warps_total * 1024 + lane * 32));
+        }
+        // ---- phase 0: 8 + 8 coalesced 128-bit loads per lane, interleaved into (x, y) pairs
 #pragma unroll
         for (int it = 0; it < 8; it++) {
             const int v4 = it * 32 + lane;                     // float4 index inside the plane
             float4 a = ipr_ldg_stream4(reinterpret_cast<const float4 *>(xg) + v4);
             float4 b = ipr_ldg_stream4(reinterpret_cast<const float4 *>(yg) + v4);
-            if (p.normalized) {
+            if (NORM) {
                 a.x = (a.x + 1.f) * .5f; a.y = (a.y + 1.f) * .5f; a.z = (a.z + 1.f) * .5f; a.w = (a.w + 1.f) * .5f;
                 b.x = (b.x + 1.f) * .5f; b.y = (b.y + 1.f) * .5f; b.z = (b.z + 1.f) * .5f; b.w = (b.w + 1.f) * .5f;
             }
-            float2 *dst = P + (v4 >> 3) * S32_P_PITCH + ((v4 & 7) << 2);
+            float2 *dst = P + (v4 >> 3) * S32_PITCH + ((v4 & 7) << 2);
             dst[0] = make_float2(a.x, b.x); dst[1] = make_float2(a.y, b.y);
             dst[2] = make_float2(a.z, b.z); dst[3] = make_float2(a.w, b.w);
         }
         __syncwarp();
-        // ---- pass 1: vertical, lane = column
+        // Every pass below streams its input line once and scatters each value into the (at most 11) outputs it
+        // feeds: 11 independent FMA chains in flight, ~11 live accumulators instead of a whole line in registers.
+        // ---- pass 1a: vertical filter of (x, y); lane = column
         {
-            float2 w[32], q[32];
+            float2 acc[22], buf[32];
+#pragma unroll
+            for (int r = 0; r < S32_PF; r++) buf[r] = P[r * S32_PITCH + lane];
 #pragma unroll
             for (int r = 0; r < 32; r++) {
-                w[r] = P[r * S32_P_PITCH + lane];
-                q[r] = make_float2(fmaf(w[r].x, w[r].x, w[r].y * w[r].y), w[r].x * w[r].y);
-            }
-#pragma unroll
-            for (int i = 0; i < 22; i++) {
-                float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k <= RAD; k++) { a = ffma2(tap2(k), w[i + k], a); b = ffma2(tap2(k), q[i + k], b); }
-                Va[i * S32_P_PITCH + lane] = a;
-                Vb[i * S32_P_PITCH + lane] = b;
-            }
-        }
-        __syncwarp();
-        // ---- pass 2: horizontal + SSIM map + derivatives, lane = row (22 active)
-        float ssum = 0.f;
-        if (lane < 22) {
-            float2 wa[32], wb[32];
-#pragma unroll
-            for (int c = 0; c < 32; c++) { wa[c] = Va[lane * S32_P_PITCH + c]; wb[c] = Vb[lane * S32_P_PITCH + c]; }
-#pragma unroll
-            for (int j = 0; j < 22; j++) {
-                float2 m = make_float2(0.f, 0.f), e = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k <= RAD; k++) { m = ffma2(tap2(k), wa[j + k], m); e = ffma2(tap2(k), wb[j + k], e); }
-                const float mx = m.x, my = m.y;
-                const float mxx = mx * mx, myy = my * my, mxy = mx * my;
-                const float A1 = 2.f * mxy + SSIM_C1;
-                const float B1 = mxx + myy + SSIM_C1;
-                const float A2 = 2.f * (e.y - mxy) + SSIM_C2;
-                const float B2 = (e.x - mxx - myy) + SSIM_C2;
-                const float iB1 = 1.0f / B1, iB2 = 1.0f / B2;
-                const float iB12 = iB1 * iB2;
-                const float S = A1 * A2 * iB12;
-                ssum += S;
-                if (WITH_GRAD) {
-                    Dpq[lane * S32_D_PITCH + j] = make_float2(2.f * my * (A2 - A1) * iB12 + 2.f * mx * S * (iB2 - iB1), -S * iB2);
-                    Dr[lane * S32_D_PITCH + j] = 2.f * A1 * iB12;
-                }
-            }
-        }
-        ssum = ipr_warp_sum(ssum);
-        if (lane == 0) p.partial[plane] = ssum;
-        if (!WITH_GRAD) { __syncwarp(); continue; }
-        __syncwarp();
-        // ---- pass 3: vertical transposed, lane = map column (22 active); zero taps dropped at compile time
-        if (lane < 22) {
-            float2 d[22]; float dr[22];
-#pragma unroll
-            for (int i = 0; i < 22; i++) { d[i] = Dpq[i * S32_D_PITCH + lane]; dr[i] = Dr[i * S32_D_PITCH + lane]; }
-#pragma unroll
-            for (int r = 0; r < 32; r++) {
-                float2 a = make_float2(0.f, 0.f); float b = 0.f;
+                if (r + S32_PF < 32) buf[r + S32_PF] = P[(r + S32_PF) * S32_PITCH + lane];
+                const float2 v = buf[r];
 #pragma unroll
                 for (int k = 0; k <= RAD; k++) {
                     const int i = r - k;
-                    if (i >= 0 && i < 22) { a = ffma2(tap2(k), d[i], a); b = fmaf(kTap[k], dr[i], b); }
+                    if (i >= 0 && i < 22) acc[i] = (k == 0) ? fmul2(tap2(0), v) : ffma2(tap2(k), v, acc[i]);
                 }
-                Epq[r * S32_D_PITCH + lane] = a;
-                Er[r * S32_D_PITCH + lane] = b;
+                if (r >= RAD) V[(r - RAD) * S32_PITCH + lane] = acc[r - RAD];
             }
         }
         __syncwarp();
-        // ---- pass 4: horizontal transposed + epilogue, lane = row
+        // ---- pass 2a: horizontal filter -> local means (mu_x, mu_y) kept in registers; lane = map row
+        float2 m[22];
         {
-            float2 e[22]; float er[22];
+            float2 buf[32];
 #pragma unroll
-            for (int j = 0; j < 22; j++) { e[j] = Epq[lane * S32_D_PITCH + j]; er[j] = Er[lane * S32_D_PITCH + j]; }
-            float *dxr = p.dx + plane * 1024 + lane * 32;
-            const float4 *xr = reinterpret_cast<const float4 *>(xg + lane * 32);
-            const float4 *yr = reinterpret_cast<const float4 *>(yg + lane * 32);
+            for (int c = 0; c < S32_PF; c++) buf[c] = V[l22 * S32_PITCH + c];
 #pragma unroll
-            for (int c4 = 0; c4 < 8; c4++) {
-                float4 xv = __ldg(xr + c4), yv = __ldg(yr + c4);       // L2 hits: this warp streamed them in phase 0
-                if (p.normalized) {
-                    xv.x = (xv.x + 1.f) * .5f; xv.y = (xv.y + 1.f) * .5f; xv.z = (xv.z + 1.f) * .5f; xv.w = (xv.w + 1.f) * .5f;
-                    yv.x = (yv.x + 1.f) * .5f; yv.y = (yv.y + 1.f) * .5f; yv.z = (yv.z + 1.f) * .5f; yv.w = (yv.w + 1.f) * .5f;
+            for (int c = 0; c < 32; c++) {
+                if (c + S32_PF < 32) buf[c + S32_PF] = V[l22 * S32_PITCH + c + S32_PF];
+                const float2 v = buf[c];
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    const int j = c - k;
+                    if (j >= 0 && j < 22) m[j] = (k == 0) ? fmul2(tap2(0), v) : ffma2(tap2(k), v, m[j]);
                 }
-                const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
-                float o[4];
+            }
+        }
+        __syncwarp();
+        // ---- pass 1b: vertical filter of (x^2 + y^2, x*y); lane = column
+        {
+            float2 acc[22], buf[32];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int c = c4 * 4 + u;
-                    float2 f = make_float2(0.f, 0.f); float fr = 0.f;
+            for (int r = 0; r < S32_PF; r++) buf[r] = P[r * S32_PITCH + lane];
 #pragma unroll
-                    for (int k = 0; k <= RAD; k++) {
-                        const int j = c - k;
-                        if (j >= 0 && j < 22) { f = ffma2(tap2(k), e[j], f); fr = fmaf(kTap[k], er[j], fr); }
+            for (int r = 0; r < 32; r++) {
+                if (r + S32_PF < 32) buf[r + S32_PF] = P[(r + S32_PF) * S32_PITCH + lane];
+                const float2 w = buf[r];
+                const float2 v = make_float2(fmaf(w.x, w.x, w.y * w.y), w.x * w.y);
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    const int i = r - k;
+                    if (i >= 0 && i < 22) acc[i] = (k == 0) ? fmul2(tap2(0), v) : ffma2(tap2(k), v, acc[i]);
+                }
+                if (r >= RAD) V[(r - RAD) * S32_PITCH + lane] = acc[r - RAD];
+            }
+        }
+        __syncwarp();
+        // ---- pass 2b: horizontal filter of the second moments + SSIM map + its derivatives; lane = map row
+        float ssum = 0.f;
+        {
+            float2 e[22], buf[32];
+            float *drow = Mr(l22);
+            float2 *dpqrow = Mpq(l22);
+#pragma unroll
+            for (int c = 0; c < S32_PF; c++) buf[c] = V[l22 * S32_PITCH + c];
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                if (c + S32_PF < 32) buf[c + S32_PF] = V[l22 * S32_PITCH + c + S32_PF];
+                const float2 v = buf[c];
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    const int j = c - k;
+                    if (j >= 0 && j < 22) e[j] = (k == 0) ? fmul2(tap2(0), v) : ffma2(tap2(k), v, e[j]);
+                }
+                if (c >= RAD) {
+                    const int j = c - RAD;
+                    const float mx = m[j].x, my = m[j].y;
+                    const float mxy = mx * my;
+                    const float B1 = fmaf(my, my, fmaf(mx, mx, SSIM_C1));
+                    const float A1 = fmaf(2.f, mxy, SSIM_C1);
+                    const float A2 = fmaf(2.f, e[j].y - mxy, SSIM_C2);
+                    const float B2 = (e[j].x + (SSIM_C1 + SSIM_C2)) - B1;
+                    const float iB12 = rcp_approx(B1 * B2);
+                    const float S = A1 * A2 * iB12;
+                    ssum += S;
+                    if (WITH_GRAD) {
+                        // dS/dp = 2 mu_y (A2 - A1)/(B1 B2) + 2 mu_x S (1/B2 - 1/B1);  1/B2 - 1/B1 = (B1 - B2)/(B1 B2)
+                        const float t = 2.f * iB12;
+                        const float dp = t * fmaf(my, A2 - A1, mx * S * (B1 - B2));
+                        const float dq = -S * B1 * iB12;
+                        if (act) {                             // lands on V[row][0..c+1] of this lane's own row: already read
+                            drow[j] = t * A1;
+                            dpqrow[j] = make_float2(dp, dq);
+                        }
                     }
-                    o[u] = p.coef * (f.x + 2.f * xs[u] * f.y + ys[u] * fr);
                 }
-                ipr_stg_stream4(reinterpret_cast<float4 *>(dxr) + c4, make_float4(o[0], o[1], o[2], o[3]));
+            }
+        }
+        ssum = ipr_warp_sum(act ? ssum : 0.f);
+        if (lane == 0) p.partial[plane] = ssum;
+        __syncwarp();
+        if (!WITH_GRAD) continue;
+        // ---- pass 3: vertical transposed filter; lane = map column.  E row r overlays D row r of the same lane.
+        {
+            float2 acc[32], buf[22]; float accr[32], bufr[22];
+#pragma unroll
+            for (int i = 0; i < S32_PF; i++) { buf[i] = Mpq(i)[l22]; bufr[i] = Mr(i)[l22]; }
+#pragma unroll
+            for (int i = 0; i < 22; i++) {
+                if (i + S32_PF < 22) { buf[i + S32_PF] = Mpq(i + S32_PF)[l22]; bufr[i + S32_PF] = Mr(i + S32_PF)[l22]; }
+                const float2 d = buf[i];
+                const float dr = bufr[i];
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    const int r = i + k;
+                    if (k == RAD || i == 0) { acc[r] = fmul2(tap2(k), d); accr[r] = kTap[k] * dr; }
+                    else { acc[r] = ffma2(tap2(k), d, acc[r]); accr[r] = fmaf(kTap[k], dr, accr[r]); }
+                }
+                if (act) { Mpq(i)[lane] = acc[i]; Mr(i)[lane] = accr[i]; }     // row i is complete (fed by d[i-10..i])
+            }
+            if (act) {
+#pragma unroll
+                for (int r = 22; r < 32; r++) { Mpq(r)[lane] = acc[r]; Mr(r)[lane] = accr[r]; }
+            }
+        }
+        __syncwarp();
+        // ---- pass 4: horizontal transposed filter + chain rule with (x, y) from P; lane = image row; dX parks in P.x
+        {
+            float2 acc[32], buf[22]; float accr[32], bufr[22];
+            const float2 *epq = Mpq(lane);
+            const float *er = Mr(lane);
+            float2 *prow = P + lane * S32_PITCH;
+#pragma unroll
+            for (int j = 0; j < S32_PF; j++) { buf[j] = epq[j]; bufr[j] = er[j]; }
+#pragma unroll
+            for (int j = 0; j < 22; j++) {
+                if (j + S32_PF < 22) { buf[j + S32_PF] = epq[j + S32_PF]; bufr[j + S32_PF] = er[j + S32_PF]; }
+                const float2 d = buf[j];
+                const float dr = bufr[j];
+#pragma unroll
+                for (int k = 0; k <= RAD; k++) {
+                    const int c = j + k;
+                    if (k == RAD || j == 0) { acc[c] = fmul2(tap2(k), d); accr[c] = kTap[k] * dr; }
+                    else { acc[c] = ffma2(tap2(k), d, acc[c]); accr[c] = fmaf(kTap[k], dr, accr[c]); }
+                }
+                {                                              // column j is complete
+                    const float2 xy = prow[j];
+                    prow[j].x = p.coef * fmaf(xy.y, accr[j], fmaf(2.f * xy.x, acc[j].y, acc[j].x));
+                }
+            }
+#pragma unroll
+            for (int c = 22; c < 32; c++) {
+                const float2 xy = prow[c];
+                prow[c].x = p.coef * fmaf(xy.y, accr[c], fmaf(2.f * xy.x, acc[c].y, acc[c].x));
+            }
+        }
+        __syncwarp();
+        // ---- copy-out: coalesced 128-bit stores of dX
+        {
+            float4 *dx4 = reinterpret_cast<float4 *>(p.dx + plane * 1024);
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int v4 = it * 32 + lane;
+                const float2 *src = P + (v4 >> 3) * S32_PITCH + ((v4 & 7) << 2);
+                ipr_stg_stream4(dx4 + v4, make_float4(src[0].x, src[1].x, src[2].x, src[3].x));
             }
         }
         __syncwarp();
@@ -549,24 +645,30 @@ int check_common(const float *x, const float *y, int64_t batch, int C, int H, in
     return IPR_OK;
 }
 
+template <bool WITH_GRAD, bool NORM>
+int launch_warp32_impl(const SsimParams &p, cudaStream_t st)
+{
+    constexpr int WARPS = 4;
+    const size_t smem = (size_t)WARPS * S32_WARP_BYTES;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(ssim32_warp_kernel<WITH_GRAD, NORM>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    long long ctas = (p.planes + WARPS - 1) / WARPS;
+    const long long cap = (long long)ipr_sm_count() * 3;          // 3 CTAs (12 warps) per SM, persistent over planes
+    if (ctas > cap) ctas = cap;
+    IPR_LAUNCH_PDL((ssim32_warp_kernel<WITH_GRAD, NORM>), (unsigned)ctas, WARPS * 32, smem, st, p);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
 template <bool WITH_GRAD>
 int launch_warp32(const SsimParams &p, cudaStream_t st)
 {
-    constexpr int WARPS = 4;
-    const size_t smem = (size_t)WARPS * S32_WARP_FLOATS * sizeof(float);
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[WITH_GRAD]) {
-        cudaError_t e = cudaFuncSetAttribute(ssim32_warp_kernel<WITH_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_done[WITH_GRAD] = true;
-    }
-    long long ctas = (p.planes + WARPS - 1) / WARPS;
-    const long long cap = (long long)ipr_sm_count() * 2;          // 2 CTAs (8 warps) per SM, persistent over planes
-    if (ctas > cap) ctas = cap;
-    IPR_LAUNCH_PDL((ssim32_warp_kernel<WITH_GRAD>), (unsigned)ctas, WARPS * 32, smem, st, p);
-    IPR_LAUNCH_CHECK();
-    return IPR_OK;
+    return p.normalized ? launch_warp32_impl<WITH_GRAD, true>(p, st) : launch_warp32_impl<WITH_GRAD, false>(p, st);
 }
 
 inline bool use_warp32(const SsimParams &p) {
