@@ -363,6 +363,17 @@ static_assert(S32_ROW_M == S32_PITCH * 8, "a D/E row overlays exactly one V row"
 static_assert(S32_PF >= 1, "pass 2b stores D(p,q)[j] over V[j+11], which must already be in registers");
 static_assert(S32_WARP_BYTES % 16 == 0, "warp regions stay 16-byte aligned");
 
+// The transposed passes filter three maps: packed FFMA2 for (p,q) next to scalar FFMA for r.  FFMA2 takes the FMA pipe
+// for two cycles (profiles/r1_fma_rate_probe.txt: same 128 FMA/clk/SM as scalar FFMA) but frees an issue slot for the
+// LDS/STS traffic; measured 1302 us (packed) vs 1364 us (all scalar) at 65536x3x32x32.
+#ifndef IPR_SSIM_BWD_SCALAR
+#define S32_MUL2(k, d) fmul2(tap2(k), d)
+#define S32_FMA2(k, d, a) ffma2(tap2(k), d, a)
+#else
+#define S32_MUL2(k, d) make_float2(kTap[k] * (d).x, kTap[k] * (d).y)
+#define S32_FMA2(k, d, a) make_float2(fmaf(kTap[k], (d).x, (a).x), fmaf(kTap[k], (d).y, (a).y))
+#endif
+
 template <bool WITH_GRAD, bool NORM>
 __global__ void __launch_bounds__(128, 3)
 ssim32_warp_kernel(const SsimParams p)
@@ -520,8 +531,8 @@ ssim32_warp_kernel(const SsimParams p)
 #pragma unroll
                 for (int k = 0; k <= RAD; k++) {
                     const int r = i + k;
-                    if (k == RAD || i == 0) { acc[r] = fmul2(tap2(k), d); accr[r] = kTap[k] * dr; }
-                    else { acc[r] = ffma2(tap2(k), d, acc[r]); accr[r] = fmaf(kTap[k], dr, accr[r]); }
+                    if (k == RAD || i == 0) { acc[r] = S32_MUL2(k, d); accr[r] = kTap[k] * dr; }
+                    else { acc[r] = S32_FMA2(k, d, acc[r]); accr[r] = fmaf(kTap[k], dr, accr[r]); }
                 }
                 if (act) { Mpq(i)[lane] = acc[i]; Mr(i)[lane] = accr[i]; }     // row i is complete (fed by d[i-10..i])
             }
@@ -547,8 +558,8 @@ ssim32_warp_kernel(const SsimParams p)
 #pragma unroll
                 for (int k = 0; k <= RAD; k++) {
                     const int c = j + k;
-                    if (k == RAD || j == 0) { acc[c] = fmul2(tap2(k), d); accr[c] = kTap[k] * dr; }
-                    else { acc[c] = ffma2(tap2(k), d, acc[c]); accr[c] = fmaf(kTap[k], dr, accr[c]); }
+                    if (k == RAD || j == 0) { acc[c] = S32_MUL2(k, d); accr[c] = kTap[k] * dr; }
+                    else { acc[c] = S32_FMA2(k, d, acc[c]); accr[c] = fmaf(kTap[k], dr, accr[c]); }
                 }
                 {                                              // column j is complete
                     const float2 xy = prow[j];

@@ -17,6 +17,8 @@ allocator, so a whole training step can be captured in one CUDA graph.
 """
 import ctypes
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -307,6 +309,45 @@ class DisPlans(object):
         return arr
 
 
+_SIDE_STREAMS = {}
+_USE_SIDE = os.environ.get("IPR_SIDE_STREAM", "1") != "0"
+
+
+class _Fork(object):
+    """Runs the weight-gradient GEMMs (and their split-K reductions / bias column sums) of a backward pass on a side
+    stream so that they overlap the data-gradient chain, which is the critical path.  Works the same eagerly and
+    under stream capture (the waits become graph edges).  Tensors handed to the side stream are kept alive until
+    ``join`` so the caching allocator cannot recycle them while the side stream still reads them."""
+
+    def __init__(self, device):
+        self.enabled = _USE_SIDE
+        if not self.enabled:
+            return
+        self.main = torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        self.side = _SIDE_STREAMS[key]
+        self.keep = []
+        self.used = False
+
+    def run(self, fn, *tensors):
+        if not self.enabled:
+            return fn()
+        self.side.wait_stream(self.main)            # everything enqueued so far happens-before the side work
+        with torch.cuda.stream(self.side):
+            r = fn()
+        self.keep.extend(tensors)
+        self.used = True
+        return r
+
+    def join(self):
+        if self.enabled and self.used:
+            self.main.wait_stream(self.side)
+            self.keep = []
+            self.used = False
+
+
 def _grad_dst(param):
     """Where a weight gradient goes: straight into the parameter's ``.grad`` arena view (accumulating, nothing is
     returned to autograd -- saves one add kernel and one temporary per parameter) or, without an arena, a fresh tensor
@@ -386,8 +427,9 @@ class _GeneratorFn(torch.autograd.Function):
         # last layer: Tanh' fused into the patch gather, then one GEMM for d(a3) and one for dW4
         col = im2col3(dout.contiguous(), out)
         mod_c = module.convs
+        fork = _Fork(dev)
         dw4, acc4, ret4 = _grad_dst(mod_c[3].weight)
-        P.last_wg.run(acts[3], col, dw4, accumulate=acc4)
+        fork.run(lambda: P.last_wg.run(acts[3], col, dw4, accumulate=acc4), col, dw4)
         d_act, _ = P.last_dg.run(col, P.packs.get("ct3_dg"))
         dws, dgs, dbs = [None] * 3, [None] * 3, [None] * 3
         sign_hook = getattr(module, "_ipr_sign_hook", None)
@@ -403,7 +445,7 @@ class _GeneratorFn(torch.autograd.Function):
                 sg, g0, sc = sign_hook(i)
             dx = bn_relu_bwd(d_act, raws[i], scales[i], shifts[i], gammas[i], means[i], rstds[i], dg_t, db_t, acc_g, sg, g0, sc)
             dw_t, acc_w, dws[i] = _grad_dst(mod_c[i][0].weight)
-            P.ct_wg[i].run(dx, acts[i], dw_t, accumulate=acc_w)
+            fork.run(lambda i=i, dx=dx, dw_t=dw_t, acc_w=acc_w: P.ct_wg[i].run(dx, acts[i], dw_t, accumulate=acc_w), dx, dw_t)
             wd = P.packs.get("ct%d_dg" % i)
             if i > 0:
                 d_act, _ = P.ct_dg[i].run(dx, wd)
@@ -411,10 +453,11 @@ class _GeneratorFn(torch.autograd.Function):
                 d_act, _ = P.ct_dg[i].run(dx, wd, epi=dense.EPI_MASK, slope=0.0, mask=acts[0])
         dh = d_act.view(B, 1, 1, -1)
         dfc_t, acc_fc, dfc_w = _grad_dst(module.fc[0].weight)
-        P.fc_wg.run(dh, a0, dfc_t, accumulate=acc_fc)
+        fork.run(lambda: P.fc_wg.run(dh, a0, dfc_t, accumulate=acc_fc), dh, dfc_t)
         perm = P.perm_on(dev)
         dfc_b = torch.empty(fc_w.shape[0], device=dev, dtype=torch.float32)
         dfc_b[perm] = colsum_bf16(dh.view(B, -1))
+        fork.join()
         return (None, None, dfc_w, dfc_b, dws[0], dgs[0], dbs[0], dws[1], dgs[1], dbs[1], dws[2], dgs[2], dbs[2], ret4)
 
 
@@ -488,26 +531,29 @@ class _DiscriminatorFn(torch.autograd.Function):
             gW[7] = g8.view(1, -1)
             gB[7] = dlogits.sum().view(1)
         dy = dy.view(acts[-1].shape)
+        fork = _Fork(dev)
         if want:
             dst, acc, gB[6] = _grad_dst(layers[6].bias)
-            colsum_bf16(dy.view(-1, dy.shape[-1]), out=dst, accumulate=acc)
+            fork.run(lambda dy=dy, dst=dst, acc=acc: colsum_bf16(dy.view(-1, dy.shape[-1]), out=dst, accumulate=acc), dy, dst)
         for i in range(5, -1, -1):                 # conv layers 7..2 (index i+1 in the layer list)
             li = i + 1
             if want:
                 gW[li] = torch.empty_like(ws[li])
-                P.conv_wg[i].run(dy, acts[i], gW[li])
+                fork.run(lambda i=i, dy=dy, g=gW[li]: P.conv_wg[i].run(dy, acts[i], g), dy)
             # the data-gradient GEMM's epilogue also yields the column sums of its output = the bias gradient below
             dy, st = P.conv_dg[i].run(dy, P.packs.get("c%d_dg" % li), epi=dense.EPI_MASK, slope=0.1, mask=acts[i],
                                       sigma=sig[li], want_stats=want)
             if want:
                 dst, acc, gB[i] = _grad_dst(layers[i].bias)
-                colsum_partials(st, out=dst, accumulate=acc, ncols=dy.shape[-1])
+                fork.run(lambda st=st, dst=dst, acc=acc, n=dy.shape[-1]: colsum_partials(st, out=dst, accumulate=acc, ncols=n),
+                         st, dst)
         dx = None
         if ctx.x_needs_grad:
             dx, _ = P.first_dg.run(dy, P.packs.get("c0_dg"), epi=dense.EPI_LINEAR_NCHW, sigma=sig[0], n_valid=3)
         if want:
             gW[0] = torch.empty_like(ws[0])
-            P.first_wg.run(dy, col, gW[0])
+            fork.run(lambda: P.first_wg.run(dy, col, gW[0]), dy)
+            fork.join()
             # gradients so far are w.r.t. W / sigma: one batched kernel pair turns them into d/dW_orig
             scratch = torch.empty(P.scratch_floats, device=dev, dtype=torch.float32)
             outs = []
