@@ -226,8 +226,11 @@ def run_b200(args):
     torch.cuda.synchronize()
     torch.cuda._sleep(200_000_000)               # ~0.1 s GPU spin: the host enqueues the whole step behind it, so the
     dense.PROFILE = []                           # event pairs below time back-to-back kernels, not launch gaps
+    from ipr_gan_b200 import engine as _engine
+    _side, _engine._USE_SIDE = _engine._USE_SIDE, False     # one stream: every GEMM is timed alone, not overlapped
     tr._step()
     torch.cuda.synchronize()
+    _engine._USE_SIDE = _side
     gemm_ms = sum(a.elapsed_time(b) for _, _, a, b in dense.PROFILE)
     gemm_flops = sum(f for _, f, _, _ in dense.PROFILE)
     n_gemm = len(dense.PROFILE)

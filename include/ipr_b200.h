@@ -197,11 +197,14 @@ typedef struct {
     int32_t out_sh, out_sw;
     int8_t  out_oh[IPR_TG_MAX_PHASES], out_ow[IPR_TG_MAX_PHASES];
     int32_t n_valid;               /* columns >= n_valid are not stored                              */
-    float  *stats;                 /* optional [m_tiles*n_phases][2][n_total] per-tile column sums / sums of squares */
+    float  *stats;                 /* optional [ipr_tapgemm_stats_rows()][2][n_total] partial column sums / sums of
+                                      squares; their sum over rows is the statistic (IPR_EPI_MASK: sums only) */
 } ipr_tapgemm_t;
 
-/* number of M tiles (rows of `stats` = n_phases * this) */
+/* number of M tiles of the launch described by d */
 int ipr_tapgemm_m_tiles(const ipr_tapgemm_t *d_host);
+/* rows the launch described by d writes into d->stats (every row is written; sum them) */
+int ipr_tapgemm_stats_rows(const ipr_tapgemm_t *d_host);
 int ipr_tapgemm_bf16(const ipr_tapgemm_t *d_host, ipr_stream_t stream);
 
 /* Weight gradient of a tap-GEMM layer (tcgen05, MN-major operands, split-K over pixels):

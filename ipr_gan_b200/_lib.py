@@ -53,6 +53,7 @@ SIGNATURES = {
     "ipr_pdq_hash_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr]),
     "ipr_hash_pvalue": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ipr_tapgemm_m_tiles": (c_int, [c_ptr]),
+    "ipr_tapgemm_stats_rows": (c_int, [c_ptr]),
     "ipr_tapgemm_bf16": (c_int, [c_ptr, c_ptr]),
     "ipr_wgrad_workspace_bytes": (c_size, [c_ptr]),
     "ipr_wgrad_total_kblocks": (c_int, [c_ptr]),

@@ -19,6 +19,7 @@ _SM_COUNT_TILES = 120          # want at least this many CTA tiles before wideni
 # When set to a list, every GEMM launch appends (kind, algorithmic_flops, start_event, end_event): bench.py uses
 # it for the live tensor-roofline measurement (CUDA events on the launching stream).
 PROFILE = None
+PROFILE_DETAIL = False         # scripts/gemm_detail.py: append the layer shape to the kind label
 
 
 def _prof_begin():
@@ -63,6 +64,8 @@ def _bind():
         L.ipr_tapgemm_bf16.argtypes = [ctypes.POINTER(TapGemm), ctypes.c_void_p]
         L.ipr_tapgemm_m_tiles.restype = ctypes.c_int
         L.ipr_tapgemm_m_tiles.argtypes = [ctypes.POINTER(TapGemm)]
+        L.ipr_tapgemm_stats_rows.restype = ctypes.c_int
+        L.ipr_tapgemm_stats_rows.argtypes = [ctypes.POINTER(TapGemm)]
         L._tg_bound = True
     return L
 
@@ -199,15 +202,18 @@ class Plan(object):
         d.n_valid = nv
         stats = None
         if want_stats:
-            tiles = L.ipr_tapgemm_m_tiles(ctypes.byref(d))
-            if tiles < 0:
-                check(tiles, "ipr_tapgemm_m_tiles")
-            stats = torch.empty(tiles * self.n_phases, 2, self.n_total, device=a.device, dtype=torch.float32)
+            rows = L.ipr_tapgemm_stats_rows(ctypes.byref(d))
+            if rows < 0:
+                check(rows, "ipr_tapgemm_stats_rows")
+            stats = torch.empty(rows, 2, self.n_total, device=a.device, dtype=torch.float32)
             d.stats = stats.data_ptr()
         ev = _prof_begin()
         check(L.ipr_tapgemm_bf16(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
               "ipr_tapgemm_bf16(%s)" % self.kind)
-        _prof_end("tapgemm:" + self.kind, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps * self.k_valid() * nv, ev)
+        label = "tapgemm:" + self.kind
+        if PROFILE_DETAIL:
+            label += " %d->%d rows=%d taps=%dx%d bn=%d epi=%d" % (C, self.cout, m_pix, self.n_phases, self.n_taps, block_n, epi)
+        _prof_end(label, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps * self.k_valid() * nv, ev)
         return out, stats
 
     def k_valid(self):
@@ -313,7 +319,10 @@ class WGradPlan(object):
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         ev = _prof_begin()
         check(L.ipr_wgrad_bf16(ctypes.byref(d), st), "ipr_wgrad_bf16(%s)" % self.fwd.kind)
-        _prof_end("wgrad:" + self.fwd.kind, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps *
+        label = "wgrad:" + self.fwd.kind
+        if PROFILE_DETAIL:
+            label += " %d->%d rows=%d taps=%dx%d splits=%d" % (xc, self.rows, N * d.q_h * d.q_w, self.n_phases, self.n_taps, splits)
+        _prof_end(label, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps *
                   getattr(self, "k_valid_override", xc) * getattr(self, "rows_valid_override", self.rows), ev)
         dst_off, row_map = self._tables(x.device)
         check(L.ipr_wgrad_reduce_f32(ws.data_ptr(), splits, self.n_phases, self.rows, self.k_total,
