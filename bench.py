@@ -300,7 +300,10 @@ def run_b200(args):
         "roofline_ssim": {"bound": "hbm", "unit": "GB/s", "peak": pk.get("hbm_gbs"), "peak_source": pk_src,
                           "achieved_at_step_batch": ssim_small, "achieved_at_16384": ssim_big,
                           "frac_at_16384": ssim_big / pk.get("hbm_gbs", 6650.0),
-                          "note": "36*B*H*W algorithmic bytes; the kernel is fp32-FMA-issue bound, see DESIGN.md"},
+                          "traffic": 549.2e6, "traffic_note": "ncu dram read+write of one launch at B=16384 "
+                          "(profiles/r1_ssim32_warp_kernel_full.txt); algorithmic 604 MB, 55 MB of dX still in L2",
+                          "note": "36*B*H*W algorithmic bytes; the kernel is fp32-FMA-pipe bound (60 % FMA pipe), "
+                                  "see DESIGN.md section 5"},
         "last_metrics": metrics_box.get("m"),
     }
     if not args.skip_cpu_baseline and world == 1:
