@@ -64,7 +64,7 @@ class ProtectedDCGANTrainer(object):
         engine.reset_caches()                       # weight packing must be part of the captured step
         self.graph = torch.cuda.CUDAGraph()
         # thread_local: NCCL's watchdog thread may query events while this thread captures (multi-GPU runs)
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.graph, stream=s, capture_error_mode="thread_local"):
             before = _lib.launch_count()
             self._step()
             self.launches_per_step = _lib.launch_count() - before

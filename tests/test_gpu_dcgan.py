@@ -40,7 +40,7 @@ def _pair(seed=0):
     return G.cuda(), D.cuda(), Go, Do
 
 
-@pytest.mark.parametrize("B", [8, 64])
+@pytest.mark.parametrize("B", [8, 64, 5, 1])
 def test_generator_forward_backward(B):
     G, _, Go, _ = _pair()
     z = torch.randn(B, 128)
@@ -65,7 +65,7 @@ def test_generator_forward_backward(B):
         assert rel(G(z.cuda()), Go(z)) < 2e-2
 
 
-@pytest.mark.parametrize("B", [8, 64])
+@pytest.mark.parametrize("B", [8, 64, 5, 1])
 def test_discriminator_forward_backward(B):
     _, D, _, Do = _pair(1)
     x = torch.randn(B, 3, 32, 32).clamp(-1, 1)
@@ -80,9 +80,11 @@ def test_discriminator_forward_backward(B):
     loss.backward()
     torch.relu(1 - ref).mean().backward()
     torch.relu(1 - sim).mean().backward()
-    assert rel(xg.grad, xs.grad) < MATCHED_GRAD_TOL and rel(xg.grad, xo.grad) < FP32_GRAD_SANITY
+    # LeakyReLU-mask flips are a per-element random effect: with fewer than 8 samples their relative weight grows
+    tol = MATCHED_GRAD_TOL * (1.5 if B < 8 else 1.0)
+    assert rel(xg.grad, xs.grad) < tol and rel(xg.grad, xo.grad) < FP32_GRAD_SANITY
     for (n, p), (_, q), (_, r) in zip(D.named_parameters(), Do.named_parameters(), Ds.named_parameters()):
-        assert rel(p.grad, r.grad) < MATCHED_GRAD_TOL, (n, rel(p.grad, r.grad))
+        assert rel(p.grad, r.grad) < tol, (n, rel(p.grad, r.grad))
         assert rel(p.grad, q.grad) < FP32_GRAD_SANITY, (n, rel(p.grad, q.grad))
     for (n, b), (_, c) in zip(D.named_buffers(), Do.named_buffers()):      # power-iteration state advanced alike
         assert rel(b, c) < 1e-3, n
