@@ -44,9 +44,29 @@ class DCGAN(Model):
     def forward_d(self, data):
         self.latent = data["latent"]
         self.real_sample = data["real_sample"]
+        dev = self.device[0]
+        if dev.type == "cuda" and self._concurrent():
+            # D(real) does not depend on the generator: it runs (forward and, through autograd, backward) on a second
+            # stream next to G(z) -> D(fake).  The engine keeps the reference's order for everything the two passes
+            # share: spectral-norm power iterations (real first, then fake), weight packing, gradient accumulation.
+            from ipr_gan_b200 import engine
+            main, aux = torch.cuda.current_stream(dev), engine.aux_stream(dev)
+            aux.wait_stream(main)
+            with torch.cuda.stream(aux):
+                self.real_logits = self.D(self.real_sample)
+            self.fake_sample = self.G(self.latent)
+            self.fake_logits = self.D(self.fake_sample.detach())
+            main.wait_stream(aux)
+            self.real_logits.record_stream(main)
+            return
         self.fake_sample = self.G(self.latent)
         self.real_logits = self.D(self.real_sample)
         self.fake_logits = self.D(self.fake_sample.detach())
+
+    def _concurrent(self):
+        from ipr_gan_b200 import engine
+        import os
+        return engine.concurrent_passes() and os.environ.get("IPR_NET_BACKEND", "native") == "native"
 
     def forward_g(self, data):
         self.generated = data["fake_sample"]

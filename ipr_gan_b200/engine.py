@@ -127,6 +127,19 @@ def dfc_bwd(a, w, sigma, dlogit, want_dw, slope):
 
 
 # ----------------------------------------------------------------------------------------- plan caches
+def _ev_record(stream):
+    """Event marking 'shared state updated on `stream`' (+ whether it was recorded inside a graph capture: captured
+    events only mean something inside that capture, eager ones only outside)."""
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    return ev, stream, torch.cuda.is_current_stream_capturing()
+
+
+def _ev_wait(rec, stream):
+    if rec is not None and rec[1] != stream and rec[2] == torch.cuda.is_current_stream_capturing():
+        stream.wait_event(rec[0])
+
+
 class PackSet(object):
     """Every bf16 GEMM operand layout of one network, rebuilt from the network's fp32 parameter arena by ONE
     gather launch (csrc/optim.cu) whenever the masters changed."""
@@ -150,13 +163,18 @@ class PackSet(object):
         self.index = torch.cat(parts).to(dev)
         self.buf = torch.empty(off, device=dev, dtype=torch.bfloat16)
         self.stamp = None
+        self.event = None
 
     def refresh(self):
         stamp = (self.arena.param._version, self.arena.version)
+        cur = torch.cuda.current_stream(self.buf.device)
         if stamp != self.stamp:
             check(lib().ipr_gather_pack_bf16(_p(self.arena.param), _p(self.index), _p(self.buf), self.buf.numel(), _st()),
                   "ipr_gather_pack_bf16")
             self.stamp = stamp
+            self.event = _ev_record(cur)            # other streams (concurrent D(real) / D(fake) passes) wait for the pack
+        else:
+            _ev_wait(self.event, cur)
 
     def get(self, key):
         self.refresh()
@@ -165,15 +183,33 @@ class PackSet(object):
 
     def clear(self):
         self.stamp = None
+        self.event = None
 
 
 _ALL_PACKS = []
+
+
+_SN_EVENTS = {}                # id(DisPlans) -> event after the latest power iteration (orders SN state across streams)
 
 
 def reset_caches():
     """Mark every packed-weight set stale (call before CUDA-graph capture so packing is part of the graph)."""
     for p in _ALL_PACKS:
         p.clear()
+    _SN_EVENTS.clear()
+
+
+def aux_stream(device):
+    """Second compute stream of a device: models run independent network passes (D(real) next to G -> D(fake)) on
+    it; inside a CUDA-graph capture the fork/join become graph branches."""
+    key = ("aux", device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def concurrent_passes():
+    return _USE_SIDE and os.environ.get("IPR_CONCURRENT_PASSES", "1") != "0"
 
 
 def _col_off_patch27(n_is_first):
@@ -488,9 +524,12 @@ class _DiscriminatorFn(torch.autograd.Function):
         # on the module's weight_u / weight_v buffers, then ONE copy snapshots the vectors for backward
         sigma = torch.empty(8, device=dev, dtype=torch.float32)
         scratch = torch.empty(P.scratch_floats, device=dev, dtype=torch.float32)
+        cur = torch.cuda.current_stream(dev)
+        _ev_wait(_SN_EVENTS.get(id(P)), cur)       # a pass on another stream advanced u/v: keep the reference's order
         check(lib().ipr_sn_power_iter_f32(P.sn_table(layers, P.uv, sigma), 8, int(module.training), 1e-12,
                                           _p(scratch), _st()), "ipr_sn_power_iter_f32")
         uv = P.uv.clone()
+        _SN_EVENTS[id(P)] = _ev_record(cur)
         sig = [sigma[i:i + 1] for i in range(8)]
         col = im2col3(x.detach().contiguous())
         a, _ = P.first.run(col, P.packs.get("c0"), epi=dense.EPI_BIAS_LRELU, slope=0.1, sigma=sig[0], bias=bs[0].detach())
@@ -553,17 +592,23 @@ class _DiscriminatorFn(torch.autograd.Function):
         if want:
             gW[0] = torch.empty_like(ws[0])
             fork.run(lambda: P.first_wg.run(dy, col, gW[0]), dy)
-            fork.join()
-            # gradients so far are w.r.t. W / sigma: one batched kernel pair turns them into d/dW_orig
-            scratch = torch.empty(P.scratch_floats, device=dev, dtype=torch.float32)
+            # gradients so far are w.r.t. W / sigma: one batched kernel pair turns them into d/dW_orig.  It accumulates
+            # into the gradient arena, so it runs on the shared side stream: two passes backpropagating concurrently on
+            # different streams (D(real), D(fake)) then never race on the arena.
             outs = []
             for i, l in enumerate(layers):
                 dst, acc, ret = _grad_dst(l.weight_orig)
                 outs.append(dst if acc else None)
                 if acc:
                     gW_ret[i] = None
-            check(lib().ipr_sn_weight_grad_f32(P.sn_table(layers, uv, sigma, gW, outs), 8, _p(scratch), _st()),
-                  "ipr_sn_weight_grad_f32")
+
+            def _sn_grad():
+                scratch = torch.empty(P.scratch_floats, device=dev, dtype=torch.float32)
+                check(lib().ipr_sn_weight_grad_f32(P.sn_table(layers, uv, sigma, gW, outs), 8, _p(scratch), _st()),
+                      "ipr_sn_weight_grad_f32")
+                return scratch
+            keep = fork.run(_sn_grad, *[g for g in gW if g is not None])
+            fork.join()
         grads = []
         for i in range(8):
             grads += [gW_ret[i] if (want and i in gW_ret) else gW[i], gB[i]]
