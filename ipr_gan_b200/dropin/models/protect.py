@@ -48,10 +48,29 @@ class BlackBoxWrapper(Wrapper):
             return
         source = getattr(self.model, self.config.input_var)
         produced = getattr(self.model, self.config.output_var)
+        net = getattr(self.model, self.config.target)
+        fork = getattr(self, "_fork_event", None)
+        self._fork_event = None
+        if fork is not None:
+            # the trigger pass is independent of the adversarial pass the inner model just enqueued: run it (forward
+            # and, through autograd, backward) on the second stream, forked from where update_g started
+            from ipr_gan_b200 import engine
+            dev = self.device[0]
+            main, aux = torch.cuda.current_stream(dev), engine.aux_stream(dev)
+            aux.wait_event(fork)
+            with torch.cuda.stream(aux):
+                with torch.no_grad():
+                    self.xwm = self.fn_inp(source.detach())
+                    self.ywm = self.fn_out(produced.detach())
+                with DisableBatchNormStats(net):
+                    self.Gxwm = net(self.xwm)
+            main.wait_stream(aux)
+            for t in (self.xwm, self.ywm, self.Gxwm):
+                t.record_stream(main)
+            return
         with torch.no_grad():
             self.xwm = self.fn_inp(source.detach())
             self.ywm = self.fn_out(produced.detach())
-        net = getattr(self.model, self.config.target)
         with DisableBatchNormStats(net):
             self.Gxwm = net(self.xwm)
 
@@ -63,7 +82,19 @@ class BlackBoxWrapper(Wrapper):
             metrics["G/Sum"] += self.Lambda * w
         return metrics
 
+    def _mark_fork(self):
+        """Record where update_g starts, so forward_g can fork the trigger pass from there (CUDA + native DCGAN nets;
+        `_concurrent` falls through to the wrapped model and is None for models without concurrent passes)."""
+        self._fork_event = None
+        dev = self.device[0]
+        concurrent = self._concurrent
+        if dev.type == "cuda" and concurrent is not None and concurrent():
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._fork_event = ev
+
     def update_g(self, data, update=True):
+        self._mark_fork()
         self.model.update_g(data, update=False)
         self.forward_g(data)
         self.compute_g_loss()

@@ -479,7 +479,14 @@ class _GeneratorFn(torch.autograd.Function):
             sg, g0, sc = (None, 0.0, 0.0)
             if sign_hook is not None:
                 sg, g0, sc = sign_hook(i)
-            dx = bn_relu_bwd(d_act, raws[i], scales[i], shifts[i], gammas[i], means[i], rstds[i], dg_t, db_t, acc_g, sg, g0, sc)
+            if acc_g and concurrent_passes():
+                # two generator passes (G(z), G(trigger)) may backpropagate on different streams: every accumulation
+                # into the gradient arena goes through the shared side stream, so gamma/beta gradients take a detour
+                tg, tb = torch.empty_like(gammas[i]), torch.empty_like(gammas[i])
+                dx = bn_relu_bwd(d_act, raws[i], scales[i], shifts[i], gammas[i], means[i], rstds[i], tg, tb, False, sg, g0, sc)
+                fork.run(lambda dg_t=dg_t, db_t=db_t, tg=tg, tb=tb: (dg_t.add_(tg), db_t.add_(tb)), tg, tb)
+            else:
+                dx = bn_relu_bwd(d_act, raws[i], scales[i], shifts[i], gammas[i], means[i], rstds[i], dg_t, db_t, acc_g, sg, g0, sc)
             dw_t, acc_w, dws[i] = _grad_dst(mod_c[i][0].weight)
             fork.run(lambda i=i, dx=dx, dw_t=dw_t, acc_w=acc_w: P.ct_wg[i].run(dx, acts[i], dw_t, accumulate=acc_w), dx, dw_t)
             wd = P.packs.get("ct%d_dg" % i)
