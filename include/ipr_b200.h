@@ -250,6 +250,15 @@ int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_r
 int ipr_im2col3_bf16(const float *x, const float *tanh_out, void *out, int64_t batch, int height, int width,
                      ipr_stream_t stream);
 
+/* Folds the nine taps of a 3-output-channel 3x3 layer: t = [batch*height*width][ld] fp32 (16-byte aligned,
+ * ld >= 28 and a multiple of 4, batch < 65536) with column
+ * (kh*3+kw)*3 + c holding tap (kh,kw) of channel c (produced by one plain GEMM over the 64-channel activation),
+ * out[b][c][h][w] = act(sum_{kh,kw} t[(b, h+1-kh, w+1-kw)][(kh*3+kw)*3+c]), act = tanh if tanh_out else identity.
+ * This is ConvTranspose2d(64,3,3,1,1)+Tanh of networks/conv_generator.py:21-22 and the input gradient of
+ * Conv2d(3,64,3,1,1) of networks/sn_discriminator.py:15. */
+int ipr_col2im3_f32(const float *t, float *out, int64_t batch, int height, int width, int ld, int tanh_out,
+                    ipr_stream_t stream);
+
 /* BatchNorm2d training-mode statistics (networks/conv_generator.py:9): partial = [rows][2][C] column sums and
  * sums of squares produced by the GEMM epilogue; count = elements per channel.  Writes scale = gamma*rstd,
  * shift = beta - mean*scale, mean, rstd and (if running_mean != NULL) updates the running statistics with

@@ -409,8 +409,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 } else if (p.epi_mode == IPR_EPI_LINEAR_F32) {
                     float *o = reinterpret_cast<float *>(p.out) + pix * p.out_c + n0;
+                    if (n0 + CH <= p.n_valid && (p.out_c & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < CH; j++) if (n0 + j < p.n_valid) o[j] = v[j];
+                        for (int j4 = 0; j4 < CH / 4; j4++)
+                            reinterpret_cast<float4 *>(o)[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CH; j++) if (n0 + j < p.n_valid) o[j] = v[j];
+                    }
                 } else {
                     __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_c + n0;
                     if (n0 + CH <= p.n_valid) {

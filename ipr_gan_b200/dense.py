@@ -213,7 +213,8 @@ class Plan(object):
         label = "tapgemm:" + self.kind
         if PROFILE_DETAIL:
             label += " %d->%d rows=%d taps=%dx%d bn=%d epi=%d" % (C, self.cout, m_pix, self.n_phases, self.n_taps, block_n, epi)
-        _prof_end(label, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps * self.k_valid() * nv, ev)
+        _prof_end(label, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps * self.k_valid() *
+                  getattr(self, "n_valid_flops", nv), ev)
         return out, stats
 
     def k_valid(self):

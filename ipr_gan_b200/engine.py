@@ -46,6 +46,15 @@ def im2col3(x, tanh_out=None):
     return out
 
 
+def col2im3(t, tanh_out):
+    """t: (B, H, W, ld) fp32 tap-expanded GEMM output -> (B, 3, H, W) fp32 (see csrc/nn_misc.cu: col2im3_kernel)."""
+    B, H, W, ld = t.shape
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    out = torch.empty(B, 3, H, W, device=t.device, dtype=torch.float32)
+    check(lib().ipr_col2im3_f32(_p(t), _p(out), B, H, W, ld, int(bool(tanh_out)), _st()), "ipr_col2im3_f32")
+    return out
+
+
 def colsum_partials(partial, out=None, accumulate=False, scale=1.0, ncols=None):
     """partial: [rows][row_stride] fp32 -> out[ncols] = column sums of the first ``ncols`` columns (fixed order)."""
     rows, stride = partial.shape[0], partial.numel() // partial.shape[0]
@@ -230,6 +239,14 @@ def _patch27_layout(w):
     return m
 
 
+def _tap27_rows_layout(w):
+    """(64, 3, 3, 3)-shaped weight whose first dimension is the contraction (ConvT (I, 3, kh, kw): I; Conv (O, 3, kh,
+    kw) in its input gradient: O) -> [1][32][64]: row (kh*3+kw)*3 + c, column k; rows 27..31 are zero."""
+    m = torch.zeros(1, 32, 64, device=w.device, dtype=w.dtype)
+    m[0, :27] = w.permute(2, 3, 1, 0).reshape(27, 64)
+    return m
+
+
 class GenPlans(object):
     def __init__(self, module):
         mg = module.mg
@@ -245,7 +262,8 @@ class GenPlans(object):
         self.ct = [dense.Plan("convT4s2", ci, co) for ci, co in zip(chans[:-1], chans[1:])]
         self.ct_dg = [dense.Plan("convT4s2_dgrad", co, ci) for ci, co in zip(chans[:-1], chans[1:])]
         self.ct_wg = [dense.WGradPlan(p, (p.cin, p.cout, 4, 4)) for p in self.ct]
-        self.last = dense.Plan("convT3", 64, 3, n_pad=16)
+        self.last = dense.Plan("linear", 64, 32)                       # tap-expanded last layer, folded by col2im3
+        self.last.n_valid_flops = 27
         self.last_dg = dense.Plan("linear", 64, 64)                    # d(a3) = patches(dY) x W'
         self.last_wg = dense.WGradPlan(dense.Plan("linear", 64, 64), (64, 3, 3, 3), col_off=_col_off_patch27(True),
                                        s_n=27)
@@ -258,7 +276,7 @@ class GenPlans(object):
         for i in range(3):
             specs.append(("ct%d" % i, cv[i][0].weight, self.ct[i].pack_layout))
             specs.append(("ct%d_dg" % i, cv[i][0].weight, self.ct_dg[i].pack_layout))
-        specs.append(("ct3", cv[3].weight, self.last.pack_layout))
+        specs.append(("ct3", cv[3].weight, _tap27_rows_layout))
         specs.append(("ct3_dg", cv[3].weight, _patch27_layout))
         self.packs = PackSet(module, specs)
         _ALL_PACKS.append(self.packs)
@@ -279,7 +297,8 @@ class DisPlans(object):
         self.first = dense.Plan("linear", 64, 64)                      # patches(x) x W1
         self.first_wg = dense.WGradPlan(dense.Plan("linear", 64, 64), (64, 3, 3, 3), col_off=_col_off_patch27(False),
                                         s_n=27)
-        self.first_dg = dense.Plan("conv3_dgrad", 64, 3, n_pad=16)
+        self.first_dg = dense.Plan("linear", 64, 32)                   # tap-expanded input gradient, folded by col2im3
+        self.first_dg.n_valid_flops = 27
         self.first.k_valid_override = 27
         self.first_wg.k_valid_override = 27
         self.conv = [dense.Plan(k, ci, co) for k, ci, co in specs]
@@ -291,7 +310,7 @@ class DisPlans(object):
         self.perm = (c * (md * md) + hw).reshape(-1)                    # NHWC feature n' -> reference feature
         self._perm_dev = {}
         layers = _sn_layers(module)
-        pk = [("c0", layers[0].weight_orig, _patch27_layout), ("c0_dg", layers[0].weight_orig, self.first_dg.pack_layout)]
+        pk = [("c0", layers[0].weight_orig, _patch27_layout), ("c0_dg", layers[0].weight_orig, _tap27_rows_layout)]
         for i in range(6):
             pk.append(("c%d" % (i + 1), layers[i + 1].weight_orig, self.conv[i].pack_layout))
             pk.append(("c%d_dg" % (i + 1), layers[i + 1].weight_orig, self.conv_dg[i].pack_layout))
@@ -442,7 +461,8 @@ class _GeneratorFn(torch.autograd.Function):
             rstds.append(rstd)
             scales.append(scale)
             shifts.append(shift)
-        out, _ = P.last.run(acts[-1], P.packs.get("ct3"), epi=dense.EPI_TANH_NCHW, n_valid=3)
+        t9, _ = P.last.run(acts[-1], P.packs.get("ct3"), epi=dense.EPI_LINEAR_F32, n_valid=32)
+        out = col2im3(t9, True)
         ctx.module = module
         ctx.save_for_backward(a0, out, fc_w, w1, w2, w3, w4, g1, g2, g3, *acts, *raws, *means, *rstds, *scales, *shifts)
         return out
@@ -595,7 +615,8 @@ class _DiscriminatorFn(torch.autograd.Function):
                          st, dst)
         dx = None
         if ctx.x_needs_grad:
-            dx, _ = P.first_dg.run(dy, P.packs.get("c0_dg"), epi=dense.EPI_LINEAR_NCHW, sigma=sig[0], n_valid=3)
+            t9, _ = P.first_dg.run(dy, P.packs.get("c0_dg"), epi=dense.EPI_LINEAR_F32, sigma=sig[0], n_valid=32)
+            dx = col2im3(t9, False)
         if want:
             gW[0] = torch.empty_like(ws[0])
             fork.run(lambda: P.first_wg.run(dy, col, gW[0]), dy)

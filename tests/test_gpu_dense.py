@@ -146,3 +146,28 @@ def test_weight_gradients(kind, B, C, O, H):
     close(grad, w.grad, tol=5e-3)
     wg.run(dya, xa, grad, accumulate=True, scale=0.5, splits=3)
     close(grad, 1.5 * w.grad, tol=5e-3)
+
+
+@pytest.mark.parametrize("B,H", [(8, 32), (3, 32), (5, 16)])
+def test_tap_expanded_three_channel_layers(B, H):
+    """The 3-channel ends: one plain GEMM to 27 (tap, channel) columns + col2im3 fold, against
+    ConvTranspose2d(64,3,3,1,1)+Tanh (generator) and the input gradient of Conv2d(3,64,3,1,1) (discriminator)."""
+    from ipr_gan_b200 import dense, engine
+    torch.manual_seed(B * H)
+    plan = dense.Plan("linear", 64, 32)
+    a = torch.randn(B, 64, H, H, device="cuda")
+    # generator: weight (I=64, O=3, kh, kw)
+    wt = torch.randn(64, 3, 3, 3, device="cuda") * 0.1
+    t9, _ = plan.run(nhwc(a), engine._tap27_rows_layout(wt).to(torch.bfloat16), epi=dense.EPI_LINEAR_F32, n_valid=32)
+    got = engine.col2im3(t9, True)
+    want = torch.tanh(F.conv_transpose2d(bf(a), bf(wt), stride=1, padding=1))
+    assert got.shape == (B, 3, H, H)
+    close(got, want, tol=2e-3)
+    # discriminator: weight (O=64, C=3, kh, kw), dy has 64 channels; dx = conv_transpose2d(dy, W) / sigma
+    wc = torch.randn(64, 3, 3, 3, device="cuda") * 0.1
+    sigma = torch.tensor(2.5, device="cuda")
+    t9, _ = plan.run(nhwc(a), engine._tap27_rows_layout(wc).to(torch.bfloat16), epi=dense.EPI_LINEAR_F32, sigma=sigma,
+                     n_valid=32)
+    got = engine.col2im3(t9, False)
+    want = F.conv_transpose2d(bf(a), bf(wc), stride=1, padding=1) / 2.5
+    close(got, want, tol=2e-3)
