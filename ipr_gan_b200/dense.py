@@ -57,6 +57,7 @@ class TapGemm(ctypes.Structure):
     ]
 
 
+
 def _bind():
     L = lib()
     if not getattr(L, "_tg_bound", False):
@@ -312,7 +313,7 @@ class WGradPlan(object):
             tiles = L.ipr_wgrad_tiles(ctypes.byref(d))           # one CTA per SM (48 KB stages): fill the chip once
             # one CTA per SM (about 190 KB of smem stages): never exceed one wave, a second partial wave doubles the time
             slots = _SM_COUNT * _WGRAD_OVERSUB
-            splits = max(1, min(kblocks // 4 if kblocks >= 8 else 1, slots // tiles, 128))
+            splits = max(1, min(kblocks // 4 if kblocks >= 8 else 1, slots // tiles, _SM_COUNT))
         d.splits = splits
         nbytes = L.ipr_wgrad_workspace_bytes(ctypes.byref(d))
         ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
