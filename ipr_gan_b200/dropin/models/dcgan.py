@@ -55,13 +55,20 @@ class DCGAN(Model):
             with torch.cuda.stream(aux):
                 self.real_logits = self.D(self.real_sample)
             self.fake_sample = self.G(self.latent)
-            self.fake_logits = self.D(self.fake_sample.detach())
+            self._d_on_fake()
             main.wait_stream(aux)
             self.real_logits.record_stream(main)
             return
         self.fake_sample = self.G(self.latent)
         self.real_logits = self.D(self.real_sample)
-        self.fake_logits = self.D(self.fake_sample.detach())
+        self._d_on_fake()
+
+    def _d_on_fake(self):
+        fake = self.fake_sample.detach()
+        self.fake_logits = self.D(fake)
+        col = getattr(fake, "_ipr_col", None)       # patch matrix of the image: update_g's D(generated) reuses it
+        if col is not None:
+            self.fake_sample._ipr_col = col
 
     def _concurrent(self):
         from ipr_gan_b200 import engine

@@ -558,7 +558,17 @@ class _DiscriminatorFn(torch.autograd.Function):
         uv = P.uv.clone()
         _SN_EVENTS[id(P)] = _ev_record(cur)
         sig = [sigma[i:i + 1] for i in range(8)]
-        col = im2col3(x.detach().contiguous())
+        # D(fake.detach()) and D(generated) see the same image in one step: the model hands the patch matrix over on
+        # the tensor object itself (dropin/models/dcgan.py), so its lifetime is the image's lifetime
+        stash = getattr(x, "_ipr_col", None)
+        if stash is not None and stash[1] == x._version and stash[0].shape[0] == B and stash[0].device == dev:
+            col = stash[0]
+        else:
+            col = im2col3(x.detach().contiguous())
+            try:
+                x._ipr_col = (col, x._version)     # an in-place edit of the image bumps _version and voids it
+            except Exception:
+                pass
         a, _ = P.first.run(col, P.packs.get("c0"), epi=dense.EPI_BIAS_LRELU, slope=0.1, sigma=sig[0], bias=bs[0].detach())
         acts = [a]
         for i, plan in enumerate(P.conv):
