@@ -177,7 +177,7 @@ int ipr_hash_pvalue(const uint32_t *hx, const uint32_t *hy, const float *ptable,
  * Replaces the cuDNN / cuBLAS calls under networks/conv_generator.py:8,13,21 and networks/sn_discriminator.py:9-21. */
 typedef struct {
     const void *a;                 /* bf16 NHWC activations, 16-byte aligned                         */
-    int32_t a_n, a_h, a_w, a_c;    /* a_c multiple of 64                                             */
+    int32_t a_n, a_h, a_w, a_c;    /* a_c multiple of 64 (single-tap layers: multiple of 8, zero-extended) */
     int32_t a_parity;
     int32_t q_h, q_w;              /* virtual output grid per image; q_w*q_h divides or is divided by 128 */
     const void *b;                 /* bf16 [n_phases][n_total][n_taps*a_c]                           */
@@ -243,7 +243,7 @@ int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_r
 
 /* ------------------------------------------------------------------ memory-bound layers around the GEMMs */
 
-/* out[(n,h,w)][k] (bf16, 64 columns) = x[n, c, h+kh-1, w+kw-1] for k = (kh*3+kw)*3 + c < 27, else 0;
+/* out[(n,h,w)][k] (bf16, 32 columns = 64-byte rows) = x[n, c, h+kh-1, w+kw-1] for k = (kh*3+kw)*3 + c < 27, else 0;
  * x: (batch, 3, H, W) fp32 NCHW.  tanh_out (optional, same shape): x is multiplied by (1 - tanh_out^2)
  * (Tanh backward of networks/conv_generator.py:22 fused into the gather).  Feeds the first discriminator
  * convolution (networks/sn_discriminator.py:15, Cin = 3) and the last generator layer's gradients. */

@@ -533,7 +533,9 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     IPR_REQUIRE(d, IPR_E_NULL);
     IPR_REQUIRE(d->a && d->b && d->out, IPR_E_NULL);
     IPR_REQUIRE(d->a_n > 0 && d->a_h > 0 && d->a_w > 0 && d->a_c > 0, IPR_E_SHAPE);
-    IPR_REQUIRE(d->a_c % BLOCK_K == 0, IPR_E_UNSUPPORTED);
+    // channels are consumed in 64-wide boxes; a single-tap layer may store fewer (a multiple of 8): the rest of the box
+    // is TMA out-of-bounds zero fill on both operands (the 27-column patch matrices are stored 32 wide)
+    IPR_REQUIRE(d->a_c % BLOCK_K == 0 || (d->n_taps == 1 && d->a_c % 8 == 0), IPR_E_UNSUPPORTED);
     IPR_REQUIRE(d->n_taps >= 1 && d->n_taps <= IPR_TG_MAX_TAPS && d->n_phases >= 1 && d->n_phases <= IPR_TG_MAX_PHASES,
                 IPR_E_SHAPE);
     IPR_REQUIRE(d->block_n == 16 || d->block_n == 32 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256,
@@ -550,7 +552,7 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     int rc = tile_geometry(d, p);
     if (rc != IPR_OK) return rc;
     p.a_n = d->a_n; p.q_h = d->q_h; p.q_w = d->q_w;
-    p.a_c = d->a_c; p.c_chunks = d->a_c / BLOCK_K; p.n_taps = d->n_taps; p.n_total = d->n_total;
+    p.a_c = d->a_c; p.c_chunks = (d->a_c + BLOCK_K - 1) / BLOCK_K; p.n_taps = d->n_taps; p.n_total = d->n_total;
     p.n_phases = d->n_phases;
     for (int ph = 0; ph < IPR_TG_MAX_PHASES; ph++) {
         for (int t = 0; t < IPR_TG_MAX_TAPS; t++) {

@@ -30,7 +30,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------ im2col3
-// out[(n,h,w)][k], k = (kh*3+kw)*3 + c  <-  x[n, c, h+kh-1, w+kw-1] (zero outside), k in [27,64) = 0.
+// out[(n,h,w)][k], k = (kh*3+kw)*3 + c  <-  x[n, c, h+kh-1, w+kw-1] (zero outside), k in [27,32) = 0: 64-byte rows.
+// The GEMMs read them through 64-channel TMA boxes whose upper half is out-of-bounds zero fill.
 // With `t` given (tanh output), the source value is x * (1 - t^2): the Tanh backward of the generator's
 // last layer fused into the gather.
 __global__ void __launch_bounds__(256)
@@ -66,7 +67,7 @@ im2col3_kernel(const float *__restrict__ x, const float *__restrict__ t, uint4 *
                     v[(kh * 3 + kw) * 3 + c] = val;
                 }
             }
-        uint4 *dst = out + p * 8;
+        uint4 *dst = out + p * 4;
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             float f[8];
@@ -74,9 +75,6 @@ im2col3_kernel(const float *__restrict__ x, const float *__restrict__ t, uint4 *
             for (int i = 0; i < 8; i++) f[i] = v[g * 8 + i];
             dst[g] = pack8(f);
         }
-        const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int g = 4; g < 8; g++) dst[g] = z;
     }
 }
 

@@ -138,6 +138,7 @@ wgrad_kernel(const __grid_constant__ Maps maps, const WgParams p)
         for (int c0 = 0; c0 < 64 * X_UNITS; c0 += 32) {
             const int unit = unit0 + (c0 >> 6);
             if (unit >= p.n_units) break;
+            if (unit * 64 + (c0 & 63) >= p.k_total) break;      // narrow single-tap layers: columns past x_c are zero fill
             uint32_t raw[32];
             if (num_kb > 0) {
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
@@ -301,7 +302,8 @@ extern "C" int ipr_wgrad_bf16(const ipr_wgrad_t *d, ipr_stream_t stream)
     IPR_REQUIRE(d, IPR_E_NULL);
     IPR_REQUIRE(d->y && d->x && d->workspace, IPR_E_NULL);
     IPR_REQUIRE(d->n_imgs > 0 && d->y_c > 0 && d->x_c > 0 && d->splits > 0, IPR_E_SHAPE);
-    IPR_REQUIRE(d->x_c % 64 == 0 && d->y_c % 8 == 0, IPR_E_UNSUPPORTED);
+    // X channels are consumed in 64-wide units; a single-tap layer may store fewer (TMA zero-fills the rest)
+    IPR_REQUIRE((d->x_c % 64 == 0 || (d->n_taps == 1 && d->x_c % 8 == 0)) && d->y_c % 8 == 0, IPR_E_UNSUPPORTED);
     IPR_REQUIRE(d->n_taps >= 1 && d->n_taps <= IPR_TG_MAX_TAPS && d->n_phases >= 1 && d->n_phases <= IPR_TG_MAX_PHASES,
                 IPR_E_SHAPE);
     IPR_REQUIRE(ipr_aligned16(d->y) && ipr_aligned16(d->x) && ipr_aligned16(d->workspace), IPR_E_ALIGN);
@@ -309,7 +311,7 @@ extern "C" int ipr_wgrad_bf16(const ipr_wgrad_t *d, ipr_stream_t stream)
     int rc = geometry(d, p);
     if (rc != IPR_OK) return rc;
     p.n_imgs = d->n_imgs; p.q_h = d->q_h; p.q_w = d->q_w;
-    p.y_c = d->y_c; p.x_c = d->x_c; p.x_chunks = d->x_c / 64; p.n_taps = d->n_taps;
+    p.y_c = d->y_c; p.x_c = d->x_c; p.x_chunks = (d->x_c + 63) / 64; p.n_taps = d->n_taps;
     p.n_units = d->n_taps * p.x_chunks; p.n_phases = d->n_phases;
     p.kb_per_split = (p.total_kb + d->splits - 1) / d->splits;
     p.ws = d->workspace;
@@ -343,7 +345,7 @@ extern "C" int ipr_wgrad_bf16(const ipr_wgrad_t *d, ipr_stream_t stream)
 extern "C" int ipr_wgrad_tiles(const ipr_wgrad_t *d)
 {
     if (!d) return IPR_E_NULL;
-    const int n_units = d->n_taps * (d->x_c / 64);
+    const int n_units = d->n_taps * ((d->x_c + 63) / 64);
     const int xu = wgrad_x_units(n_units);
     return ((d->y_c + 127) / 128) * ((n_units + xu - 1) / xu) * d->n_phases;
 }

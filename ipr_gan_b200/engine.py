@@ -41,7 +41,7 @@ def _p(t):
 def im2col3(x, tanh_out=None):
     B, C, H, W = x.shape
     assert C == 3 and x.dtype == torch.float32 and x.is_contiguous()
-    out = torch.empty(B, H, W, 64, device=x.device, dtype=torch.bfloat16)
+    out = torch.empty(B, H, W, 32, device=x.device, dtype=torch.bfloat16)
     check(lib().ipr_im2col3_bf16(_p(x), _p(tanh_out), _p(out), B, H, W, _st()), "ipr_im2col3_bf16")
     return out
 
@@ -223,7 +223,7 @@ def concurrent_passes():
 
 def _col_off_patch27(n_is_first):
     """Column table for the 3-channel im2col layers: k = (kh*3+kw)*3 + c  ->  offset inside a (., 3, 3, 3) weight row."""
-    off = torch.full((1, 64), -1, dtype=torch.int32)
+    off = torch.full((1, 32), -1, dtype=torch.int32)
     for kh in range(3):
         for kw in range(3):
             for c in range(3):
@@ -232,9 +232,9 @@ def _col_off_patch27(n_is_first):
 
 
 def _patch27_layout(w):
-    """(n, 3, 3, 3)-shaped weight -> [1][64][64]: row n, column k = (kh*3+kw)*3 + c (conv: c = in channel of an
-    (O, 3, kh, kw) weight; convT: c = out channel of an (I, 3, kh, kw) weight)."""
-    m = torch.zeros(1, 64, 64, device=w.device, dtype=w.dtype)
+    """(n, 3, 3, 3)-shaped weight -> [1][64][32]: row n, column k = (kh*3+kw)*3 + c (conv: c = in channel of an
+    (O, 3, kh, kw) weight; convT: c = out channel of an (I, 3, kh, kw) weight); columns 27..31 are zero."""
+    m = torch.zeros(1, 64, 32, device=w.device, dtype=w.dtype)
     m[0, :, :27] = w.permute(0, 2, 3, 1).reshape(64, 27)
     return m
 
@@ -264,8 +264,8 @@ class GenPlans(object):
         self.ct_wg = [dense.WGradPlan(p, (p.cin, p.cout, 4, 4)) for p in self.ct]
         self.last = dense.Plan("linear", 64, 32)                       # tap-expanded last layer, folded by col2im3
         self.last.n_valid_flops = 27
-        self.last_dg = dense.Plan("linear", 64, 64)                    # d(a3) = patches(dY) x W'
-        self.last_wg = dense.WGradPlan(dense.Plan("linear", 64, 64), (64, 3, 3, 3), col_off=_col_off_patch27(True),
+        self.last_dg = dense.Plan("linear", 32, 64)                    # d(a3) = patches(dY) x W'  (patches stored 32 wide)
+        self.last_wg = dense.WGradPlan(dense.Plan("linear", 32, 64), (64, 3, 3, 3), col_off=_col_off_patch27(True),
                                        s_n=27)
         self.last_dg.k_valid_override = 27            # flop accounting: 27 of the 64 patch columns carry data
         self.last_wg.k_valid_override = 27
@@ -294,8 +294,8 @@ class DisPlans(object):
         self.md = md
         specs = [("conv4s2", 64, 64), ("conv3", 64, 128), ("conv4s2", 128, 128), ("conv3", 128, 256),
                  ("conv4s2", 256, 256), ("conv3", 256, 512)]
-        self.first = dense.Plan("linear", 64, 64)                      # patches(x) x W1
-        self.first_wg = dense.WGradPlan(dense.Plan("linear", 64, 64), (64, 3, 3, 3), col_off=_col_off_patch27(False),
+        self.first = dense.Plan("linear", 32, 64)                      # patches(x) x W1  (patches stored 32 wide)
+        self.first_wg = dense.WGradPlan(dense.Plan("linear", 32, 64), (64, 3, 3, 3), col_off=_col_off_patch27(False),
                                         s_n=27)
         self.first_dg = dense.Plan("linear", 64, 32)                   # tap-expanded input gradient, folded by col2im3
         self.first_dg.n_valid_flops = 27
