@@ -241,6 +241,14 @@ int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_r
                          const int32_t *dst_off, const int32_t *row_map, int64_t s_n, float *grad,
                          int accumulate, float scale, ipr_stream_t stream);
 
+/* The same reduction for plain Conv2d / ConvTranspose2d weights, destination-major (contiguous writes):
+ *     grad[n*s_n + c*s_c + j] (+)= scale * sum_splits ws[split][p][n][t*x_c + c],   tap_of_host[j] = p*n_taps + t
+ * for j < kk = phases*n_taps (<= 16).  Conv2d (O,I,kh,kw): s_n = I*kk, s_c = kk; ConvTranspose2d (I,O,kh,kw):
+ * s_n = kk, s_c = O*kk.  tap_of_host is a HOST array (passed to the kernel by value). */
+int ipr_wgrad_reduce_taps_f32(const float *workspace, int splits, int phases, int n_rows, int n_taps, int x_c,
+                              const int32_t *tap_of_host, int kk, int64_t s_n, int64_t s_c, float *grad,
+                              int accumulate, float scale, ipr_stream_t stream);
+
 /* ------------------------------------------------------------------ memory-bound layers around the GEMMs */
 
 /* out[(n,h,w)][k] (bf16, 32 columns = 64-byte rows) = x[n, c, h+kh-1, w+kw-1] for k = (kh*3+kw)*3 + c < 27, else 0;

@@ -76,6 +76,8 @@ SIGNATURES = {
     "ipr_gather_pack_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ipr_wgrad_tiles": (c_int, [c_ptr]),
     "ipr_wgrad_reduce_f32": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_int, c_f32, c_ptr]),
+    "ipr_wgrad_reduce_taps_f32": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_int, c_i64, c_i64, c_ptr, c_int,
+                                          ctypes.c_float, c_ptr]),
 }
 
 _lib = None

@@ -196,6 +196,58 @@ wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int phases, int n_
     *dst = accumulate ? *dst + acc * scale : acc * scale;
 }
 
+// Same reduction for plain convolution weights, destination-major: one thread per (row n, input channel c) gathers the
+// kk = kh*kw taps of that weight slice from the partials (coalesced along c) and writes them as ONE contiguous run
+// grad[n*s_n + c*s_c + 0..kk) -- Conv2d (O,I,kh,kw): s_n = I*kk, s_c = kk; ConvTranspose2d (I,O,kh,kw): s_n = kk,
+// s_c = O*kk.  The element-major kernel above scatters 4-byte read-modify-writes (57 us for the 512->256 k4 layer).
+struct TapOf { int v[16]; };                      // destination tap j -> phase * n_taps + tap
+
+__global__ void __launch_bounds__(256)
+wgrad_reduce_taps_kernel(const float *__restrict__ ws, int splits, int phases, int n_rows, int n_pad, int n_taps, int x_c,
+                         TapOf tap_of, int kk, long long s_n, long long s_c, float *__restrict__ grad, int accumulate,
+                         float scale)
+{
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n_rows * x_c) return;
+    const int c = (int)(e % x_c), n = (int)(e / x_c);
+    const int k_total = n_taps * x_c;
+    const size_t split_stride = (size_t)phases * n_pad * k_total;
+    float *dst = grad + (size_t)n * s_n + (size_t)c * s_c;
+    float out[16];
+    size_t src_off[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int pt = tap_of.v[j < kk ? j : 0], ph = pt / n_taps, t = pt - ph * n_taps;
+        src_off[j] = ((size_t)ph * n_pad + n) * k_total + (size_t)t * x_c + c;
+        out[j] = 0.0f;
+    }
+    for (int sp = 0; sp < splits; sp++) {             // 16 independent loads in flight per split, fixed summation order
+        const float *base = ws + (size_t)sp * split_stride;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = j < kk ? base[src_off[j]] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; j++) out[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) out[j] *= scale;
+    if (kk == 16 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            float4 v = make_float4(out[4 * g], out[4 * g + 1], out[4 * g + 2], out[4 * g + 3]);
+            if (accumulate) { const float4 o = d4[g]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            d4[g] = v;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (j < kk) dst[j] = accumulate ? dst[j] + out[j] : out[j];
+    }
+}
+
 // tile configuration: IPR_WGRAD_CFG = 0: N=128, 3 stages (2 CTAs/SM) | 1: N=128, 6 stages | 2: N=256, 4 stages | 3: N=64, 8 stages.
 // Measured on B200 (scripts/wg_sweep.sh): the MN-major tcgen05.mma stream, not the operand loads, paces this kernel
 // (skipping the TMA loads entirely only drops c3 from 45 to 37 us), and two co-resident CTAs interleave their MMA
@@ -348,6 +400,24 @@ extern "C" int ipr_wgrad_tiles(const ipr_wgrad_t *d)
     const int n_units = d->n_taps * ((d->x_c + 63) / 64);
     const int xu = wgrad_x_units(n_units);
     return ((d->y_c + 127) / 128) * ((n_units + xu - 1) / xu) * d->n_phases;
+}
+
+extern "C" int ipr_wgrad_reduce_taps_f32(const float *workspace, int splits, int phases, int n_rows, int n_taps, int x_c,
+                                         const int32_t *tap_of_host, int kk, int64_t s_n, int64_t s_c, float *grad,
+                                         int accumulate, float scale, ipr_stream_t stream)
+{
+    IPR_REQUIRE(workspace && tap_of_host && grad, IPR_E_NULL);
+    IPR_REQUIRE(splits > 0 && phases > 0 && n_rows > 0 && n_taps > 0 && x_c > 0 && kk > 0 && kk <= 16 &&
+                kk == phases * n_taps, IPR_E_SHAPE);
+    TapOf t;
+    for (int j = 0; j < 16; j++) t.v[j] = j < kk ? tap_of_host[j] : 0;
+    for (int j = 0; j < kk; j++) IPR_REQUIRE(t.v[j] >= 0 && t.v[j] < phases * n_taps, IPR_E_SHAPE);
+    const int n_pad = ((n_rows + 127) / 128) * 128;
+    const long long total = (long long)n_rows * x_c;
+    IPR_LAUNCH_PDL((wgrad_reduce_taps_kernel), (unsigned)((total + 255) / 256), 256, 0, ipr_cu(stream), workspace, splits, phases,
+                   n_rows, n_pad, n_taps, x_c, t, kk, (long long)s_n, (long long)s_c, grad, accumulate, scale);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
 }
 
 extern "C" int ipr_wgrad_reduce_f32(const float *workspace, int splits, int phases, int n_rows, int k_total,

@@ -258,6 +258,7 @@ class WGradPlan(object):
         self.x_c = fwd.cin
         self.k_total = self.n_taps * self.x_c
         self.row_perm = row_perm
+        self._plain = col_off is None and k != "linear"
         if col_off is None:
             col_off = torch.full((self.n_phases, self.k_total), -1, dtype=torch.int32)
             if k == "linear":
@@ -276,6 +277,26 @@ class WGradPlan(object):
         self.s_n = int(s_n)
         self.dst_off_host = col_off.reshape(-1).to(torch.int32).contiguous()   # [phase * k_total + k] -> offset in a row
         self._dev = {}
+        # plain conv / convT weights: destination-major reduction (contiguous writes), tap j = kh*ksz + kw <- (phase, tap)
+        self.tap_of = None
+        if self._plain:
+            ksz = weight_shape[-1]
+            kk = ksz * ksz
+            tap_of = [-1] * kk
+            for ph, taps in enumerate(fwd.taps):
+                for t, (_, _, _, kh, kw) in enumerate(taps):
+                    tap_of[kh * ksz + kw] = ph * self.n_taps + t
+            # only where it pays: big weight matrices (enough (n, c) threads) -- small ones with many splits are
+            # faster element-major
+            if kk == self.n_phases * self.n_taps and min(tap_of) >= 0 and row_perm is None and \
+                    self.rows * self.x_c >= 32768 and \
+                    __import__('os').environ.get('IPR_WGRAD_REDUCE_TAPS', '1') != '0':
+                self.tap_of = (ctypes.c_int32 * kk)(*tap_of)
+                self.kk = kk
+                if k == "convT4s2":
+                    self.s_n_t, self.s_c_t = kk, weight_shape[1] * kk
+                else:
+                    self.s_n_t, self.s_c_t = weight_shape[1] * kk, kk
 
     def _tables(self, device):
         key = str(device)
@@ -326,6 +347,11 @@ class WGradPlan(object):
             label += " %d->%d rows=%d taps=%dx%d splits=%d" % (xc, self.rows, N * d.q_h * d.q_w, self.n_phases, self.n_taps, splits)
         _prof_end(label, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps *
                   getattr(self, "k_valid_override", xc) * getattr(self, "rows_valid_override", self.rows), ev)
+        if self.tap_of is not None:
+            check(L.ipr_wgrad_reduce_taps_f32(ws.data_ptr(), splits, self.n_phases, self.rows, self.n_taps, self.x_c,
+                                              self.tap_of, self.kk, self.s_n_t, self.s_c_t, grad.data_ptr(),
+                                              int(bool(accumulate)), float(scale), st), "ipr_wgrad_reduce_taps_f32")
+            return grad
         dst_off, row_map = self._tables(x.device)
         check(L.ipr_wgrad_reduce_f32(ws.data_ptr(), splits, self.n_phases, self.rows, self.k_total,
                                      dst_off.data_ptr(),
