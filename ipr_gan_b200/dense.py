@@ -289,7 +289,7 @@ class WGradPlan(object):
             # only where it pays: big weight matrices (enough (n, c) threads) -- small ones with many splits are
             # faster element-major
             if kk == self.n_phases * self.n_taps and min(tap_of) >= 0 and row_perm is None and \
-                    self.rows * self.x_c >= 32768 and \
+                    self.rows * self.x_c >= int(__import__("os").environ.get("IPR_WGRAD_TAPS_MIN", "32768")) and \
                     __import__('os').environ.get('IPR_WGRAD_REDUCE_TAPS', '1') != '0':
                 self.tap_of = (ctypes.c_int32 * kk)(*tap_of)
                 self.kk = kk
