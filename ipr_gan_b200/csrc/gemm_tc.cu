@@ -11,10 +11,10 @@
 //   2x2 taps (blockIdx.z), so no multiplication by an inserted zero is ever issued.
 // * 128-byte swizzled K-major smem tiles feed tcgen05.mma (M=128, N=BLOCK_N, K=16 per instruction);
 //   one elected thread issues, tcgen05.commit releases smem stages / signals the epilogue.
-// * warp roles: warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer (+ TMEM allocator) (the epilogue of the
-//   low-K layers is latency-bound per warp: 8 warps halve its time per tile)
-//   (tcgen05.ld 32 lanes x 32 columns, fused 1/sigma, bias, LeakyReLU / activation-gradient mask /
-//   tanh, bf16 pack, per-column sum and sum-of-squares for BatchNorm).
+// * warp roles: warps 0..EW-1 epilogue (EW = 4 or 8, chosen per launch), then the TMA producer and the MMA issuer
+//   (+ TMEM allocator) on the two highest warp ids.  Epilogue: tcgen05.ld 32 lanes x 32 columns, fused 1/sigma, bias,
+//   LeakyReLU / activation-gradient mask / tanh, bf16 pack, per-column sum and sum-of-squares (BatchNorm statistics,
+//   bias gradients) accumulated per CTA and warp.
 // * persistent: one CTA per SM walks the tile list; the accumulator is double-buffered in TMEM (2 x BLOCK_N columns)
 //   so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1, and the TMA producer never drains between
 //   tiles (6-8 smem stages, ~190 KB).
@@ -208,7 +208,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         __syncwarp();
     } else if (warp < EPI_ACTIVE) {
-        // ===================== epilogue (warps 2..9) =====================
+        // ===================== epilogue (warps 0..EPI_ACTIVE-1) =====================
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
         const int c_begin = (warp >> 2) * CH_PER_WARP * CH, c_end = c_begin + CH_PER_WARP * CH;   // this warp's columns
         const int row = q * 32 + lane;                    // row of the 128-row tile
