@@ -291,6 +291,9 @@ def run_b200(args):
         "gpu_launches": int(tr.launches_per_step or 0) * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf, "traffic": None,
+                     "traffic_note": "aggregate over all GEMM launches of a step (tensor-bound): no single per-launch DRAM "
+                                     "figure; a representative launch (ConvT 512->256, batch 512) reads 12.7 MB from DRAM "
+                                     "with the tensor pipe 55 % active (profiles/r1_tapgemm256_convT512_full.txt)",
                      "kernel": "tapgemm_kernel + wgrad_kernel (tcgen05 implicit GEMM), %d launches/step" % n_gemm,
                      "peak_source": pk_src + " bf16_tflops_sustained",
                      "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms,
