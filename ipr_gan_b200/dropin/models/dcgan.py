@@ -72,8 +72,7 @@ class DCGAN(Model):
 
     def _concurrent(self):
         from ipr_gan_b200 import engine
-        import os
-        return engine.concurrent_passes() and os.environ.get("IPR_NET_BACKEND", "native") == "native"
+        return engine.concurrent_passes()
 
     def forward_g(self, data):
         self.generated = data["fake_sample"]

@@ -5,18 +5,20 @@
   SNDiscriminator   networks/sn_discriminator.py:4-38 net.{0,1,2}.{0,2}.{bias,weight_orig,weight_u,weight_v},
                     net.3.*, net.6.*   (legacy torch.nn.utils.spectral_norm state)
 
-The child modules are the parameter / state containers.  On a CUDA device ``forward`` does not call
-them: the whole network runs as one autograd node over the library's implicit-GEMM (tcgen05) and
-normalisation kernels (``ipr_gan_b200.engine``), NHWC/bf16 inside, NCHW/fp32 at the module boundary.
+The child modules are ONLY the parameter / state containers: ``forward`` never calls them.  The whole network runs
+as one autograd node over the library's implicit-GEMM (tcgen05) and normalisation kernels
+(``ipr_gan_b200.engine``), NHWC/bf16 inside, NCHW/fp32 at the module boundary.  There is no CPU or PyTorch-op
+path: a non-CUDA input raises (the modules can still be built, moved and (de)serialised on the CPU).
 """
-import os
-
 import torch.nn as nn
 from torch.nn.utils import spectral_norm as _sn
 
 
-def _backend():
-    return os.environ.get("IPR_NET_BACKEND", "native")
+def _require_cuda(t, who):
+    if not t.is_cuda:
+        from ipr_gan_b200.ops import IprError
+        raise IprError("%s.forward computes on CUDA only (libipr_b200.so, sm_100a); got a %s tensor -- move the "
+                       "module and its input to a CUDA device" % (who, t.device.type))
 
 
 class ConvGenerator(nn.Module):
@@ -34,10 +36,9 @@ class ConvGenerator(nn.Module):
         self.convs = nn.Sequential(*stages)
 
     def forward(self, z):
-        if z.is_cuda and _backend() == "native":
-            from ipr_gan_b200 import engine
-            return engine.generator_forward(self, z)
-        return self.convs(self.fc(z).view(z.size(0), -1, self.mg, self.mg))
+        _require_cuda(z, "ConvGenerator")
+        from ipr_gan_b200 import engine
+        return engine.generator_forward(self, z)
 
 
 class Flatten(nn.Module):
@@ -59,10 +60,9 @@ class SNDiscriminator(nn.Module):
                                  Flatten(), _sn(nn.Linear(512 * md * md, 1)))
 
     def forward(self, x):
-        if x.is_cuda and _backend() == "native":
-            from ipr_gan_b200 import engine
-            return engine.discriminator_forward(self, x)
-        return self.net(x).view(-1)
+        _require_cuda(x, "SNDiscriminator")
+        from ipr_gan_b200 import engine
+        return engine.discriminator_forward(self, x)
 
 
 def ConvGenerator32():

@@ -59,6 +59,22 @@ def test_no_cpu_fallback():
         import tools
         with pytest.raises(ops.IprError):
             tools.compute_matching_prob(torch.rand(2, 3, 16, 16), torch.rand(2, 3, 16, 16))
+    # the networks are state containers on the CPU: their forward has no PyTorch-op path either
+    import networks
+    with pytest.raises(ops.IprError):
+        networks.ConvGenerator32()(torch.randn(2, 128))
+    with pytest.raises(ops.IprError):
+        networks.SNDiscriminator32()(x)
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    """A missing libipr_b200.so is an error at the first call, never a silent fallback."""
+    from ipr_gan_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libipr_b200.so"))
+    with pytest.raises(Exception) as e:
+        _lib.lib()
+    assert "libipr_b200" in str(e.value)
 
 
 def test_dropin_surface():
