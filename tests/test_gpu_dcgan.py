@@ -187,3 +187,30 @@ def test_layer_kernels_exact():
     da, dw = engine.dfc_bwd(a, w, sig, dl, True, 0.1)
     assert rel(da, (dl[:, None] * w[None, :] / 1.3 * torch.where(a.float() > 0, 1.0, 0.1))) < 5e-3
     assert rel(dw, (dl[:, None] * a.float()).sum(0)) < 1e-5
+
+
+def test_stream_schedules_are_bit_identical(monkeypatch):
+    """The three-stream schedule (side stream for weight gradients, aux stream for D(real) / the trigger pass) only
+    reorders independent work: metrics and parameters after two steps are bit-identical to the single-stream run."""
+    from ipr_gan_b200 import engine
+    from ipr_gan_b200.trainer import ProtectedDCGANTrainer
+    g = torch.Generator().manual_seed(7)
+    batches = [(torch.randn(48, 3, 32, 32, generator=g).clamp(-1, 1), torch.randn(48, 128, generator=g)) for _ in range(2)]
+
+    def run(side, concurrent):
+        monkeypatch.setattr(engine, "_USE_SIDE", side)
+        monkeypatch.setenv("IPR_CONCURRENT_PASSES", "1" if concurrent else "0")
+        tr = ProtectedDCGANTrainer(48, torch.device("cuda", 0), use_graph=False)
+        out = []
+        for real, z in batches:
+            tr.set_inputs(real, z)
+            tr._step()
+            out.append(tr.model.get_metrics())
+        torch.cuda.synchronize()
+        params = [p.detach().clone() for p in list(tr.model.G.parameters()) + list(tr.model.D.parameters())]
+        return out, params
+
+    m0, p0 = run(False, False)
+    m1, p1 = run(True, True)
+    assert m0 == m1
+    assert all(torch.equal(a, b) for a, b in zip(p0, p1))
