@@ -143,3 +143,53 @@ def test_three_channel_tables():
     r = engine._tap27_rows_layout(w)
     assert r.shape == (1, 32, 64) and torch.all(r[0, 27:] == 0)
     assert torch.equal(r[0, (1 * 3 + 2) * 3 + 1], w[:, 1, 1, 2])            # row (kh=1, kw=2, c=1) holds W[:, 1, 1, 2]
+
+
+def _emulate_gather_pack(arena_values, index):
+    """What csrc/optim.cu: gather_pack_kernel does: out[i] = bf16(arena[index[i]]), 0 where index < 0."""
+    out = torch.zeros(index.numel(), dtype=torch.float32)
+    ok = index >= 0
+    out[ok] = arena_values[index[ok].long()]
+    return out
+
+
+def test_one_launch_packing_tables_cover_every_layer():
+    """engine.PackSet derives ONE gather table per network from the layers' layout functions applied to parameter
+    indices.  Executed on the CPU, the table must reproduce every layer's packed bf16 operand from the flat parameter
+    arena (the kernel itself is a plain gather, csrc/optim.cu)."""
+    import networks
+    torch.manual_seed(5)
+    G, D = networks.ConvGenerator32(), networks.SNDiscriminator32()
+    for module, plans_cls in ((G, engine.GenPlans), (D, engine.DisPlans)):
+        plans = plans_cls(module)
+        packs = plans.packs
+        flat_params = packs.arena.param.detach().reshape(-1)
+        packed = _emulate_gather_pack(flat_params, packs.index.cpu())
+        checked = 0
+        for key, (off, n, shape) in packs.slices.items():
+            got = packed[off:off + n].view(shape)
+            # recompute the layout directly from the parameter values with the same layout function
+            want = None
+            if plans_cls is engine.GenPlans:
+                cv = module.convs
+                table = {"fc": (module.fc[0].weight, lambda w: plans.fc.pack_layout(w, plans.perm)),
+                         "ct3": (cv[3].weight, engine._tap27_rows_layout), "ct3_dg": (cv[3].weight, engine._patch27_layout)}
+                for i in range(3):
+                    table["ct%d" % i] = (cv[i][0].weight, plans.ct[i].pack_layout)
+                    table["ct%d_dg" % i] = (cv[i][0].weight, plans.ct_dg[i].pack_layout)
+                param, fn = table[key]
+                want = fn(param.detach())
+            else:
+                layers = engine._sn_layers(module)
+                if key == "c0":
+                    want = engine._patch27_layout(layers[0].weight_orig.detach())
+                elif key == "c0_dg":
+                    want = engine._tap27_rows_layout(layers[0].weight_orig.detach())
+                else:
+                    i = int(key[1:].split("_")[0])
+                    plan = plans.conv_dg[i - 1] if key.endswith("_dg") else plans.conv[i - 1]
+                    want = plan.pack_layout(layers[i].weight_orig.detach())
+            assert got.shape == want.shape, key
+            assert torch.equal(got, want.float()), key
+            checked += 1
+        assert checked == len(packs.slices) and checked >= 9
