@@ -165,7 +165,7 @@ def run_b200(args):
     assert args.batch % world == 0
     local_batch = args.batch // world
 
-    from ipr_gan_b200 import _lib, dense
+    from ipr_gan_b200 import dense
     from ipr_gan_b200.trainer import ProtectedDCGANTrainer
     tr = ProtectedDCGANTrainer(local_batch, device, use_graph=not args.no_graph)
     gen = torch.Generator().manual_seed(1234 + rank)

@@ -10,7 +10,6 @@ import ctypes
 
 import torch
 
-from . import _lib
 from ._lib import check, lib
 
 MAX_TAPS, MAX_PHASES = 16, 4

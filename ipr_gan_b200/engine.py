@@ -20,7 +20,6 @@ import ctypes
 import os
 
 import torch
-import torch.nn as nn
 
 from . import dense, flat
 from ._lib import SnLayer
