@@ -19,10 +19,17 @@ DROPIN_DIR = os.path.join(PKG_DIR, "dropin")
 _NAMES = ("tools", "models", "networks", "configs", "pytorch_msssim")
 
 
-def enable_dropin():
+def enable_dropin(reference_root=None):
     """Make ``import tools, models, networks, configs, pytorch_msssim`` resolve to this package's
     drop-in modules.  Idempotent.  Raises if modules of those names were already imported from
-    somewhere else (e.g. the reference tree) -- mixing the two silently would void parity claims."""
+    somewhere else (e.g. the reference tree) -- mixing the two silently would void parity claims.
+
+    ``reference_root``: the ipr-gan checkout whose out-of-scope modules (``networks.InceptionActivations``,
+    ``models.VAE`` ...) the drop-in packages pass through to (default: found on ``sys.path`` / the working
+    directory / ``$IPR_REFERENCE_ROOT``, see ``ipr_gan_b200.refpath``)."""
+    if reference_root is not None:
+        from . import refpath
+        refpath.set_reference_root(reference_root)
     root = os.path.dirname(PKG_DIR)
     for p in (root, DROPIN_DIR):
         if p in sys.path:

@@ -3,7 +3,7 @@ callable ``(x, y) -> 0-dim tensor`` differentiable in ``x`` (tools/loss.py:8-20,
 
 ``ssim`` is the hot one (watermark reconstruction loss, models/wrappers.py:40): forward AND backward
 run in ONE fused sm_100a kernel pass (csrc/ssim.cu); autograd only scales the stored gradient.
-``l1`` / ``mse`` are used by no protected config and stay as PyTorch ops on the caller's device.
+``l1`` / ``mse`` / ``ms_ssim`` are used by no protected config and stay as PyTorch ops on the caller's device.
 """
 import torch
 from torch.nn import L1Loss, MSELoss
@@ -67,7 +67,7 @@ def ssim(normalized=False):
 
 
 def ms_ssim(normalized=False):
-    # used by no shipped config: outside the accelerated path, fail loudly
-    def _unsupported(x, y):
-        raise NotImplementedError("ms_ssim is not on the IPR-GAN hot path; use loss_fn: 'ssim'")
-    return _Denorm(_unsupported, normalized)
+    # selected by no shipped config: outside the accelerated path, plain PyTorch composition
+    import pytorch_msssim
+    fn = pytorch_msssim.MS_SSIM(data_range=1)
+    return _Denorm(lambda x, y: 1 - fn(x, y), normalized)

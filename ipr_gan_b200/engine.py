@@ -174,7 +174,12 @@ class PackSet(object):
         self.event = None
 
     def refresh(self):
-        stamp = (self.arena.param._version, self.arena.version)
+        # Parameters are views of the arena with their OWN version counters (flat.py: ``p.data = view``), so an
+        # in-place write to one of them (load_state_dict, a stock torch optimizer, ``w[idx] = 0``) never shows in
+        # ``arena.param._version``: stamp every parameter.  Writes through ``p.data`` bypass version counting
+        # altogether -- callers that do that (sign_flip.py:74 does, before its first forward) call
+        # ``engine.reset_caches()`` afterwards.
+        stamp = (self.arena.version, self.arena.param._version) + tuple(p._version for p in self.arena.params)
         cur = torch.cuda.current_stream(self.buf.device)
         if stamp != self.stamp:
             check(lib().ipr_gather_pack_bf16(_p(self.arena.param), _p(self.index), _p(self.buf), self.buf.numel(), _st()),
@@ -429,6 +434,9 @@ def _plans(module, cls):
 class _GeneratorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, z, fc_w, fc_b, w1, g1, b1, w2, g2, b2, w3, g3, b3, w4):
+        if z.requires_grad:
+            raise RuntimeError("ConvGenerator: a latent that requires grad is not on the IPR-GAN path (the node "
+                               "returns no gradient for z); detach it")
         P = _plans(module, GenPlans)
         B = z.shape[0]
         mg = P.mg
@@ -442,7 +450,10 @@ class _GeneratorFn(torch.autograd.Function):
         ctx.eval_stats = False
         for i in range(3):
             bn = bns[i]
-            batch_stats = bn.training or not bn.track_running_stats or bn.running_mean is None
+            # torch's rule (nn.BatchNorm2d.forward): batch statistics in training mode, or when there are no running
+            # buffers at all.  DisableBatchNormStats (models/util.py:55-69) only clears ``track_running_stats`` -- the
+            # buffers stay, so an eval-mode generator keeps using them; in training mode it stops them being updated.
+            batch_stats = bn.training or (bn.running_mean is None and bn.running_var is None)
             raw, stats = P.ct[i].run(acts[-1], P.packs.get("ct%d" % i), want_stats=batch_stats)
             if batch_stats:
                 count = raw.numel() // raw.shape[-1]

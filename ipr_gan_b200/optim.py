@@ -15,9 +15,14 @@ from ._lib import check, lib
 
 
 class FlatAdam(torch.optim.Adam):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, **ignored):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, **other):
         if amsgrad:
             raise NotImplementedError("FlatAdam: amsgrad is not on the IPR-GAN path")
+        # options that do not change the arithmetic are accepted, anything else is refused (never silently dropped)
+        harmless = {"capturable": None, "foreach": None, "fused": None, "differentiable": False, "maximize": False}
+        for k, v in other.items():
+            if k not in harmless or (harmless[k] is not None and v != harmless[k]):
+                raise NotImplementedError("FlatAdam: option %s=%r is not on the IPR-GAN path" % (k, v))
         params = list(params)
         super().__init__(params, lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         if len(self.param_groups) != 1:
@@ -38,7 +43,20 @@ class FlatAdam(torch.optim.Adam):
                              "exp_avg_sq": self._v[o:o + n].view(p.shape)}
 
     def zero_grad(self, set_to_none=True):
+        """Zeroes the gradient arena (the ``.grad`` views stay bound).  Unlike ``torch.optim.Adam`` a parameter that
+        receives no gradient in a step is therefore updated with a zero gradient (its moments decay) instead of being
+        skipped; every parameter of G and D receives a gradient in every IPR-GAN step, so the two agree on the path."""
         self.arena.zero_grad()
+
+    def state_dict(self):
+        """``torch.optim.Adam`` format with one independent CPU ``step`` tensor per parameter: the single device-side
+        counter all parameters share here must not leave as one aliased tensor (a stock Adam resuming from it would
+        advance it once per parameter)."""
+        sd = super().state_dict()
+        step = self._step.detach().to("cpu", copy=True)
+        # the packed per-parameter dicts are the live ``self.state`` entries: re-wrap, never mutate them
+        sd["state"] = {k: dict(st, step=step.clone()) for k, st in sd["state"].items()}
+        return sd
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
@@ -60,6 +78,9 @@ class FlatAdam(torch.optim.Adam):
         loss = closure() if closure is not None else None
         g = self.param_groups[0]
         arena = self.arena
+        if not arena.valid():
+            raise RuntimeError("FlatAdam: the parameters were moved out of their arena (module.to() / a new p.data "
+                               "after the optimizer was built); rebuild the optimizer")
         arena.bind_grads()
         dist.allreduce_mean_(arena.grad)            # no-op for a single process
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
