@@ -89,11 +89,12 @@ size_t ipr_ssim_workspace_bytes(int64_t batch, int channels, int height, int wid
  * single-CTA launch that adds the per-CTA partial sums in a fixed order (deterministic).
  * Replaces Loss.__call__ + ssim() (tools/loss.py:10-20, 82-85) -> pytorch_msssim.SSIM(data_range=1)
  * forward AND its autograd backward.  11-tap sigma-1.5 valid separable window; H, W >= 11.
- * dx may be NULL (forward only). */
+ * dx may be NULL (forward only).  The value stored is loss * loss_scale (1 for the plain loss; 1/world when the
+ * scalar lands in a metrics slot that a summing data-parallel all-reduce turns into the global mean). */
 int ipr_ssim_fwd_bwd_f32(const float *x, const float *y, float *dx, float *loss,
                          void *workspace, size_t workspace_bytes,
                          int64_t batch, int channels, int height, int width,
-                         int normalized, float grad_scale, ipr_stream_t stream);
+                         int normalized, float grad_scale, float loss_scale, ipr_stream_t stream);
 
 /* out[n] = mean_{c, valid map} SSIM(x[n], y[n])  (data_range 1, no de-normalisation).
  * Replaces pytorch_msssim.ssim(wm_x, wm_y, data_range=1, size_average=False)
@@ -118,9 +119,11 @@ typedef struct {
  * accumulate != 0 adds into grad instead of overwriting (fused-arena use).
  * `layers_host` is a HOST array of n_layers (<= IPR_SIGN_MAX_LAYERS) entries; it is copied into the
  * kernel parameters, so it may be freed right after the call.
+ * grad pointers may be NULL (loss only: the gradient then rides in the BatchNorm backward, ipr_bn_relu_bwd_bf16);
+ * the value stored is loss * loss_scale.
  * Replaces SignLossModel.forward (tools/sign_model.py:42-49) and its backward. */
 int ipr_sign_loss_fwd_bwd_f32(const ipr_sign_layer_t *layers_host, int n_layers, float gamma0,
-                              float grad_scale, int accumulate, float *loss, ipr_stream_t stream);
+                              float grad_scale, int accumulate, float loss_scale, float *loss, ipr_stream_t stream);
 
 /* counts[0] = #{c : sign(gamma_c) != sign_c} (gamma == 0 counts as wrong), counts[1] = total bits.
  * Replaces SignLossModel.compute_ber (tools/sign_model.py:51-60); integer, bit-exact. */
@@ -297,9 +300,12 @@ int ipr_bn_relu_bwd_bf16(const void *dy, const void *xraw, const float *scale, c
  * a: [batch][K] bf16, w: fp32 [K] in the activation's (NHWC) feature order. */
 int ipr_dfc_fwd_bf16(const void *a, const float *w, const float *sigma, const float *bias, float *logits,
                      int batch, int k, ipr_stream_t stream);
-/* da[b,k] = dlogit[b]*w[k]/sigma * (a[b,k] > 0 ? 1 : slope)   (bf16);  dw[k] (+)= sum_b dlogit[b]*a[b,k] (optional). */
+/* da[b,k] = dlogit[b]*w[k]/sigma * (a[b,k] > 0 ? 1 : slope)   (bf16);  dw[j] (+)= sum_b dlogit[b]*a[b,k] (optional),
+ * j = dw_index ? dw_index[k] : k (scatter from the NHWC feature order back to the parameter's own order);
+ * *dbias += sum_b dlogit[b] (optional, only together with dw; always accumulating, atomically). */
 int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigma, const float *dlogit, void *da, float *dw,
-                     int accumulate_dw, float slope, int batch, int k, ipr_stream_t stream);
+                     int accumulate_dw, float slope, int batch, int k, const int32_t *dw_index, float *dbias,
+                     ipr_stream_t stream);
 
 /* Column sums: out[c] (+)= scale * sum_r in[r*row_stride + c], c < ncols.  `_partials_f32` reduces fp32 partial rows (the GEMM epilogue's
  * per-warp column statistics); `_bf16` reduces an NHWC bf16 tensor over its pixels (bias gradients).
@@ -307,8 +313,10 @@ int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigma, const fl
 size_t ipr_colsum_workspace_bytes(int ncols);
 int ipr_colsum_partials_f32(const float *partial, int rows, int ncols, int row_stride, float *out, int accumulate,
                             float scale, void *workspace, size_t workspace_bytes, ipr_stream_t stream);
+/* `_bf16`: out_index (optional) redirects column c to out[out_index[c]]; accumulate == 2 adds atomically (for two
+ * producers on different streams: two float contributions onto a zeroed slot are order-independent). */
 int ipr_colsum_bf16(const void *x, int64_t rows, int channels, float *out, int accumulate, float scale,
-                    void *workspace, size_t workspace_bytes, ipr_stream_t stream);
+                    const int32_t *out_index, void *workspace, size_t workspace_bytes, ipr_stream_t stream);
 
 /* ------------------------------------------------------------------ spectral norm, optimizer, weight packing */
 
@@ -322,6 +330,8 @@ typedef struct {
     int32_t rows, cols;
     int64_t scratch_off;   /* offset (floats) of this layer's private slice of `scratch`,
                               at least ipr_sn_scratch_floats(rows, cols) long                               */
+    float *u_snap, *v_snap; /* optional: ipr_sn_power_iter_f32 also writes the vectors it leaves in u / v here
+                              (the copy one forward keeps for its backward while the buffers move on)        */
 } ipr_sn_layer_t;
 
 size_t ipr_sn_scratch_floats(int rows, int cols);
@@ -334,12 +344,33 @@ int ipr_sn_weight_grad_f32(const ipr_sn_layer_t *layers_host, int n_layers, floa
 
 /* Adam (torch.optim.Adam semantics, models/dcgan.py:21-24) over flat fp32 arenas in one launch; *step (device
  * float) is read then incremented on the device, so the call is CUDA-graph replayable. */
-int ipr_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
-                      float beta1, float beta2, float eps, float weight_decay, float *step, ipr_stream_t stream);
+/* grad_scale multiplies every gradient element first (1/world after a summing all-reduce); zero_grad != 0 clears
+ * the gradient arena as it is consumed (the next step's optimizer.zero_grad() then has nothing left to do);
+ * *ticket is a zero-initialised device word the launch uses to publish step + 1 once every CTA has read step. */
+int ipr_adam_flat_f32(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, int zero_grad,
+                      float *step, uint32_t *ticket, ipr_stream_t stream);
 
 /* dst[i] = bf16(index[i] >= 0 ? src[index[i]] : 0), n % 8 == 0: rebuilds every GEMM operand layout of a network
  * from its fp32 parameter arena in one launch. */
-int ipr_gather_pack_bf16(const float *src, const int32_t *index, void *dst, int64_t n, ipr_stream_t stream);
+/* The same launch also fills an fp32 side table dst_f32[i] = src[index_f32[i]] (n_f32 may be 0): permuted copies of
+ * the few parameters kernels read in fp32 (Linear bias in NHWC feature order, the final GEMV row). */
+int ipr_gather_pack_bf16(const float *src, const int32_t *index, void *dst, int64_t n, const int32_t *index_f32,
+                         float *dst_f32, int64_t n_f32, ipr_stream_t stream);
+
+/* ---- scalar ends of the step (csrc/step_misc.cu) ------------------------------------------------------------
+ * Hinge discriminator loss (models/dcgan.py:31-35): losses[0..2] = LossD, LossR, LossF with
+ * LossR = mean relu(1 - real), LossF = mean relu(1 + fake); d_real / d_fake (optional) = dLossD/dlogits.
+ * Stored losses are multiplied by loss_scale (gradients are not), see ipr_ssim_fwd_bwd_f32. */
+int ipr_hinge_d_loss_f32(const float *real_logits, const float *fake_logits, int batch, float loss_scale,
+                         float *losses, float *d_real, float *d_fake, ipr_stream_t stream);
+/* Generator adversarial loss (models/dcgan.py:37-40): *loss = -mean(logits); dlogits (optional) = -1/batch. */
+int ipr_gen_adv_loss_f32(const float *logits, int batch, float loss_scale, float *loss, float *dlogits,
+                         ipr_stream_t stream);
+/* n standard-normal draws (Philox4x32-10 keyed by seed, Box-Muller); *counter (device) is the stream position and
+ * advances by ceil(n/4) per launch, *ticket a zero-initialised device word: graph-replayable latent generation
+ * replacing the host-side torch.randn + H2D copy of experiments/image_generation.py:94. */
+int ipr_randn_f32(float *out, int64_t n, uint64_t seed, uint64_t *counter, uint32_t *ticket, ipr_stream_t stream);
 
 #ifdef __cplusplus
 }

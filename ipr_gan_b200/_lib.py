@@ -21,7 +21,8 @@ SIGN_MAX_LAYERS = 64
 class SnLayer(ctypes.Structure):
     """ipr_sn_layer_t"""
     _fields_ = [("w", c_ptr), ("u", c_ptr), ("v", c_ptr), ("sigma", c_ptr), ("grad", c_ptr), ("grad_out", c_ptr),
-                ("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("scratch_off", ctypes.c_int64)]
+                ("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("scratch_off", ctypes.c_int64),
+                ("u_snap", c_ptr), ("v_snap", c_ptr)]
 
 
 class SignLayer(ctypes.Structure):
@@ -44,9 +45,9 @@ SIGNATURES = {
     "ipr_transform_var_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_ptr]),
     "ipr_ssim_workspace_bytes": (c_size, [c_i64, c_int, c_int, c_int]),
     "ipr_ssim_fwd_bwd_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_i64, c_int, c_int, c_int,
-                                     c_int, c_f32, c_ptr]),
+                                     c_int, c_f32, c_f32, c_ptr]),
     "ipr_ssim_per_sample_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_i64, c_int, c_int, c_int, c_ptr]),
-    "ipr_sign_loss_fwd_bwd_f32": (c_int, [ctypes.POINTER(SignLayer), c_int, c_f32, c_f32, c_int, c_ptr, c_ptr]),
+    "ipr_sign_loss_fwd_bwd_f32": (c_int, [ctypes.POINTER(SignLayer), c_int, c_f32, c_f32, c_int, c_f32, c_ptr, c_ptr]),
     "ipr_sign_ber_i32": (c_int, [ctypes.POINTER(SignLayer), c_int, c_ptr, c_ptr]),
     "ipr_bicubic_resize_f32": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_ptr]),
     "ipr_pdq_dct_matrix_host": (None, [c_ptr]),
@@ -65,15 +66,19 @@ SIGNATURES = {
     "ipr_bn_bwd_workspace_bytes": (c_size, [c_int]),
     "ipr_bn_relu_bwd_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_f32, c_f32, c_ptr, c_size, c_i64, c_int, c_ptr]),
     "ipr_dfc_fwd_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr]),
-    "ipr_dfc_bwd_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32, c_int, c_int, c_ptr]),
+    "ipr_dfc_bwd_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "ipr_colsum_workspace_bytes": (c_size, [c_int]),
     "ipr_colsum_partials_f32": (c_int, [c_ptr, c_int, c_int, c_int, c_ptr, c_int, c_f32, c_ptr, c_size, c_ptr]),
-    "ipr_colsum_bf16": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_f32, c_ptr, c_size, c_ptr]),
+    "ipr_colsum_bf16": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_size, c_ptr]),
     "ipr_sn_scratch_floats": (c_size, [c_int, c_int]),
     "ipr_sn_power_iter_f32": (c_int, [c_ptr, c_int, c_int, c_f32, c_ptr, c_ptr]),
     "ipr_sn_weight_grad_f32": (c_int, [c_ptr, c_int, c_ptr, c_ptr]),
-    "ipr_adam_flat_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_ptr, c_ptr]),
-    "ipr_gather_pack_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ipr_adam_flat_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_int,
+                                  c_ptr, c_ptr, c_ptr]),
+    "ipr_gather_pack_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ipr_hinge_d_loss_f32": (c_int, [c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ipr_gen_adv_loss_f32": (c_int, [c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr]),
+    "ipr_randn_f32": (c_int, [c_ptr, c_i64, ctypes.c_uint64, c_ptr, c_ptr, c_ptr]),
     "ipr_wgrad_tiles": (c_int, [c_ptr]),
     "ipr_wgrad_reduce_f32": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_int, c_f32, c_ptr]),
     "ipr_wgrad_reduce_taps_f32": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_int, c_i64, c_i64, c_ptr, c_int,

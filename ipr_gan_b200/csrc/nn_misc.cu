@@ -215,8 +215,15 @@ bn_bwd_finalize_kernel(const float *__restrict__ partial, int rows, int C, doubl
         const float sv = sign[c];
         if (gamma0 - g * sv > 0.0f) dg += -sv * sign_scale / (float)C;
     }
-    dgamma[c] = accumulate ? dgamma[c] + dg : dg;
-    dbeta[c] = accumulate ? dbeta[c] + (float)sg : (float)sg;
+    if (accumulate == 2) {
+        // two backward passes of the same network (G(z) and G(trigger)) may run on different streams: a float add of
+        // exactly two contributions onto a zeroed slot is order-independent, so the atomics stay deterministic
+        atomicAdd(dgamma + c, dg);
+        atomicAdd(dbeta + c, (float)sg);
+    } else {
+        dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+        dbeta[c] = accumulate ? dbeta[c] + (float)sg : (float)sg;
+    }
 }
 
 // pass 2: dx = a*g + b*xraw + d
@@ -290,11 +297,17 @@ dfc_bwd_data_kernel(const uint4 *__restrict__ a, const float *__restrict__ w, co
 // dw[k] (+)= sum_b dlogit[b] * a[b,k]   (w.r.t. the normalised weight); CTA = 32 columns x 8 batch lanes, fixed order
 __global__ void __launch_bounds__(256)
 dfc_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ dlogit, float *__restrict__ dw,
-                      int batch, int K, int accumulate)
+                      int batch, int K, int accumulate, const int *__restrict__ dw_index, float *__restrict__ dbias)
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
     __shared__ float sm[8][33];
+    if (dbias && blockIdx.x == 0 && threadIdx.x < 32) {          // d(bias) = sum_b dlogit[b], fixed order
+        float s = 0.0f;
+        for (int b = threadIdx.x; b < batch; b += 32) s += __ldg(dlogit + b);
+        s = ipr_warp_sum(s);
+        if (threadIdx.x == 0) atomicAdd(dbias, s);               // always accumulates (zeroed gradient arena)
+    }
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int k = blockIdx.x * 32 + tx;
     float acc = 0.0f;
@@ -305,7 +318,8 @@ dfc_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restri
     if (ty == 0 && k < K) {
 #pragma unroll
         for (int y = 1; y < 8; y++) acc += sm[y][tx];
-        dw[k] = accumulate ? dw[k] + acc : acc;
+        const int o = dw_index ? __ldg(dw_index + k) : k;            // NHWC feature -> position in the parameter
+        dw[o] = accumulate ? dw[o] + acc : acc;
     }
 }
 
@@ -480,7 +494,7 @@ extern "C" int ipr_dfc_fwd_bf16(const void *a, const float *w, const float *sigm
 
 extern "C" int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigma, const float *dlogit,
                                 void *da, float *dw, int accumulate_dw, float slope, int batch, int k,
-                                ipr_stream_t stream)
+                                const int32_t *dw_index, float *dbias, ipr_stream_t stream)
 {
     IPR_REQUIRE(a && w && dlogit && da, IPR_E_NULL);
     IPR_REQUIRE(batch > 0 && k > 0 && k % 8 == 0, IPR_E_SHAPE);
@@ -491,7 +505,7 @@ extern "C" int ipr_dfc_bwd_bf16(const void *a, const float *w, const float *sigm
     IPR_LAUNCH_CHECK();
     if (dw) {
         IPR_LAUNCH_PDL((dfc_bwd_weight_kernel), (k + 31) / 32, 256, 0, ipr_cu(stream), (const __nv_bfloat16 *)a, dlogit, dw, batch, k,
-                                                                         accumulate_dw);
+                       accumulate_dw, dw_index, dbias);
         IPR_LAUNCH_CHECK();
     }
     return IPR_OK;
@@ -544,7 +558,8 @@ colsum_small_kernel(const float *__restrict__ in, int rows, int ncols, int row_s
 }
 // stage 2: out[c] (+)= scale * sum_g in[g][c], double accumulation, fixed order
 __global__ void __launch_bounds__(256)
-colsum_stage2(const float *__restrict__ in, int rows, int ncols, float *__restrict__ out, int accumulate, float scale)
+colsum_stage2(const float *__restrict__ in, int rows, int ncols, float *__restrict__ out, int accumulate, float scale,
+              const int *__restrict__ out_index)
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
@@ -553,7 +568,9 @@ colsum_stage2(const float *__restrict__ in, int rows, int ncols, float *__restri
     double acc = 0.0;
     for (int r = 0; r < rows; r++) acc += (double)in[(size_t)r * ncols + c];
     const float v = (float)acc * scale;
-    out[c] = accumulate ? out[c] + v : v;
+    const int o = out_index ? __ldg(out_index + c) : c;
+    if (accumulate == 2) atomicAdd(out + o, v);                   // two-contribution accumulation across streams
+    else out[o] = accumulate ? out[o] + v : v;
 }
 // stage 1 for a bf16 [rows][C] tensor: each CTA owns a slab of rows; 8 channels per thread
 __global__ void __launch_bounds__(256)
@@ -599,13 +616,14 @@ extern "C" int ipr_colsum_partials_f32(const float *partial, int rows, int ncols
     dim3 grid((ncols + 31) / 32, G);
     IPR_LAUNCH_PDL((colsum_partials_stage1), grid, 256, 0, ipr_cu(stream), partial, rows, ncols, row_stride, (float *)workspace);
     IPR_LAUNCH_CHECK();
-    IPR_LAUNCH_PDL((colsum_stage2), (ncols + 255) / 256, 256, 0, ipr_cu(stream), (const float *)workspace, G, ncols, out, accumulate, scale);
+    IPR_LAUNCH_PDL((colsum_stage2), (ncols + 255) / 256, 256, 0, ipr_cu(stream), (const float *)workspace, G, ncols, out, accumulate, scale,
+                   (const int *)nullptr);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
 
 extern "C" int ipr_colsum_bf16(const void *x, int64_t rows, int channels, float *out, int accumulate, float scale,
-                               void *workspace, size_t workspace_bytes, ipr_stream_t stream)
+                               const int32_t *out_index, void *workspace, size_t workspace_bytes, ipr_stream_t stream)
 {
     IPR_REQUIRE(x && out && workspace, IPR_E_NULL);
     IPR_REQUIRE(rows > 0 && channels > 0 && channels % 8 == 0, IPR_E_SHAPE);
@@ -618,7 +636,7 @@ extern "C" int ipr_colsum_bf16(const void *x, int64_t rows, int channels, float 
     IPR_LAUNCH_PDL((colsum_bf16_stage1), grid, threads, 0, ipr_cu(stream), (const uint4 *)x, rows, c_vec, (float *)workspace);
     IPR_LAUNCH_CHECK();
     IPR_LAUNCH_PDL((colsum_stage2), (channels + 255) / 256, 256, 0, ipr_cu(stream), (const float *)workspace, G, channels, out,
-                                                                    accumulate, scale);
+                   accumulate, scale, out_index);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

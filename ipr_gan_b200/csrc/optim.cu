@@ -1,7 +1,8 @@
 // optim.cu -- flat-arena optimizer and weight re-packing.
 //   * ipr_adam_flat_f32: one launch updates EVERY parameter of a network (params / grads / moments live in four
 //     contiguous fp32 arenas), replacing torch.optim.Adam's per-tensor foreach kernels (models/dcgan.py:21-24).
-//     The step counter lives on the device so the launch is CUDA-graph replayable.
+//     The step counter lives on the device so the launch is CUDA-graph replayable; the data-parallel 1/world factor
+//     is folded in as grad_scale, and the gradient arena can be cleared as it is consumed (fused zero_grad).
 //   * ipr_gather_pack_bf16: one launch rebuilds all bf16 GEMM operand layouts of a network from the fp32 master
 //     arena through a precomputed index table (dst[i] = src[idx[i]], idx < 0 -> 0).
 #include "ipr_common.cuh"
@@ -10,12 +11,22 @@
 namespace {
 
 __global__ void __launch_bounds__(256)
-adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-                 long long n, float lr, float b1, float b2, float eps, float wd, const float *__restrict__ step)
+adam_flat_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                 long long n, float lr, float b1, float b2, float eps, float wd, float gscale, int zero_grad,
+                 float *__restrict__ step, unsigned int *__restrict__ ticket)
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
-    const float t = *step + 1.0f;
+    // every CTA reads the step counter, then takes a ticket; the CTA holding the last ticket knows all others have
+    // read the old value and publishes step + 1 -- no separate increment launch, still CUDA-graph replayable
+    __shared__ float step_sm;
+    if (threadIdx.x == 0) {
+        step_sm = *reinterpret_cast<volatile float *>(step);
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; *step = step_sm + 1.0f; }
+    }
+    __syncthreads();
+    const float t = step_sm + 1.0f;
     const float bc1 = 1.0f - powf(b1, t);
     const float bc2_sqrt = sqrtf(1.0f - powf(b2, t));
     const float step_size = lr / bc1;
@@ -24,11 +35,12 @@ adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pp = reinterpret_cast<float4 *>(p)[i];
         const float4 gg = reinterpret_cast<const float4 *>(g)[i];
+        if (zero_grad) reinterpret_cast<float4 *>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 mm = reinterpret_cast<float4 *>(m)[i], vv = reinterpret_cast<float4 *>(v)[i];
         float *pa = &pp.x; const float *ga = &gg.x; float *ma = &mm.x; float *va = &vv.x;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const float gk = ga[k] + wd * pa[k];
+            const float gk = ga[k] * gscale + wd * pa[k];
             ma[k] = b1 * ma[k] + (1.0f - b1) * gk;
             va[k] = b2 * va[k] + (1.0f - b2) * gk * gk;
             pa[k] -= step_size * ma[k] / (sqrtf(va[k]) / bc2_sqrt + eps);
@@ -38,22 +50,17 @@ adam_flat_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
         reinterpret_cast<float4 *>(v)[i] = vv;
     }
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float gk = g[i] + wd * p[i];
+        const float gk = g[i] * gscale + wd * p[i];
+        if (zero_grad) g[i] = 0.0f;
         m[i] = b1 * m[i] + (1.0f - b1) * gk;
         v[i] = b2 * v[i] + (1.0f - b2) * gk * gk;
         p[i] -= step_size * m[i] / (sqrtf(v[i]) / bc2_sqrt + eps);
     }
 }
 
-__global__ void step_increment_kernel(float *step)
-{
-    ipr_pdl_wait();
-    ipr_pdl_trigger();
-    *step += 1.0f;
-}
-
 __global__ void __launch_bounds__(256)
-gather_pack_kernel(const float *__restrict__ src, const int *__restrict__ idx, __nv_bfloat16 *__restrict__ dst, long long n)
+gather_pack_kernel(const float *__restrict__ src, const int *__restrict__ idx, __nv_bfloat16 *__restrict__ dst, long long n,
+                   const int *__restrict__ idx32, float *__restrict__ dst32, long long n32)
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
@@ -74,15 +81,20 @@ gather_pack_kernel(const float *__restrict__ src, const int *__restrict__ idx, _
         }
         reinterpret_cast<uint4 *>(dst)[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    // fp32 side table (permuted copies of the few parameters the kernels read in fp32: biases, the final GEMV row)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += stride) {
+        const int id = __ldg(idx32 + i);
+        dst32[i] = id >= 0 ? __ldg(src + id) : 0.0f;
+    }
 }
 
 }  // namespace
 
-extern "C" int ipr_adam_flat_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
-                                 float lr, float beta1, float beta2, float eps, float weight_decay, float *step,
-                                 ipr_stream_t stream)
+extern "C" int ipr_adam_flat_f32(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                                 float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                                 int zero_grad, float *step, uint32_t *ticket, ipr_stream_t stream)
 {
-    IPR_REQUIRE(param && grad && exp_avg && exp_avg_sq && step, IPR_E_NULL);
+    IPR_REQUIRE(param && grad && exp_avg && exp_avg_sq && step && ticket, IPR_E_NULL);
     IPR_REQUIRE(n > 0, IPR_E_SHAPE);
     IPR_REQUIRE(ipr_aligned16(param) && ipr_aligned16(grad) && ipr_aligned16(exp_avg) && ipr_aligned16(exp_avg_sq),
                 IPR_E_ALIGN);
@@ -90,23 +102,24 @@ extern "C" int ipr_adam_flat_f32(float *param, const float *grad, float *exp_avg
     const long long cap = (long long)ipr_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    IPR_LAUNCH_PDL((adam_flat_kernel), (unsigned)blocks, 256, 0, ipr_cu(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                                  eps, weight_decay, step);
-    IPR_LAUNCH_CHECK();
-    IPR_LAUNCH_PDL((step_increment_kernel), 1, 1, 0, ipr_cu(stream), step);
+    IPR_LAUNCH_PDL((adam_flat_kernel), (unsigned)blocks, 256, 0, ipr_cu(stream), param, grad, exp_avg, exp_avg_sq, (long long)n, lr,
+                   beta1, beta2, eps, weight_decay, grad_scale, zero_grad, step, (unsigned int *)ticket);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
 
-extern "C" int ipr_gather_pack_bf16(const float *src, const int32_t *index, void *dst, int64_t n, ipr_stream_t stream)
+extern "C" int ipr_gather_pack_bf16(const float *src, const int32_t *index, void *dst, int64_t n,
+                                    const int32_t *index_f32, float *dst_f32, int64_t n_f32, ipr_stream_t stream)
 {
     IPR_REQUIRE(src && index && dst, IPR_E_NULL);
-    IPR_REQUIRE(n > 0 && n % 8 == 0, IPR_E_SHAPE);
+    IPR_REQUIRE(n > 0 && n % 8 == 0 && n_f32 >= 0, IPR_E_SHAPE);
+    IPR_REQUIRE(n_f32 == 0 || (index_f32 && dst_f32), IPR_E_NULL);
     IPR_REQUIRE(ipr_aligned16(index) && ipr_aligned16(dst), IPR_E_ALIGN);
     long long blocks = (n / 8 + 255) / 256;
     const long long cap = (long long)ipr_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    IPR_LAUNCH_PDL((gather_pack_kernel), (unsigned)blocks, 256, 0, ipr_cu(stream), src, index, (__nv_bfloat16 *)dst, n);
+    IPR_LAUNCH_PDL((gather_pack_kernel), (unsigned)blocks, 256, 0, ipr_cu(stream), src, index, (__nv_bfloat16 *)dst, (long long)n,
+                   index_f32, dst_f32, (long long)n_f32);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

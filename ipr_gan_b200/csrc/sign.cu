@@ -13,7 +13,7 @@ struct SignTable {
 
 __global__ void __launch_bounds__(512)
 sign_loss_kernel(const __grid_constant__ SignTable tab, float gamma0, float grad_scale, int accumulate,
-                 float *__restrict__ loss)
+                 float loss_scale, float *__restrict__ loss)
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
@@ -36,7 +36,7 @@ sign_loss_kernel(const __grid_constant__ SignTable tab, float gamma0, float grad
         const float layer_sum = ipr_block_sum(part, red);
         total += layer_sum * inv_n;                            // per-layer mean, summed over layers
     }
-    if (threadIdx.x == 0 && loss) *loss = total;
+    if (threadIdx.x == 0 && loss) *loss = total * loss_scale;
 }
 
 __global__ void __launch_bounds__(512)
@@ -80,13 +80,14 @@ int fill_table(SignTable &t, const ipr_sign_layer_t *layers, int n_layers)
 }  // namespace
 
 extern "C" int ipr_sign_loss_fwd_bwd_f32(const ipr_sign_layer_t *layers_host, int n_layers, float gamma0,
-                                         float grad_scale, int accumulate, float *loss, ipr_stream_t stream)
+                                         float grad_scale, int accumulate, float loss_scale, float *loss,
+                                         ipr_stream_t stream)
 {
     SignTable t;
     int rc = fill_table(t, layers_host, n_layers);
     if (rc != IPR_OK) return rc;
     IPR_REQUIRE(loss, IPR_E_NULL);
-    IPR_LAUNCH_PDL((sign_loss_kernel), 1, 512, 0, ipr_cu(stream), t, gamma0, grad_scale, accumulate, loss);
+    IPR_LAUNCH_PDL((sign_loss_kernel), 1, 512, 0, ipr_cu(stream), t, gamma0, grad_scale, accumulate, loss_scale, loss);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

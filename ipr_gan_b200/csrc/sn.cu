@@ -60,7 +60,11 @@ sn_v_kernel(const __grid_constant__ SnTable tab, const float *__restrict__ scrat
     }
     const float tot = ipr_block_sum(ss, red);
     const float inv = 1.0f / fmaxf(sqrtf(tot), eps);
-    for (int c = threadIdx.x; c < L.cols; c += blockDim.x) L.v[c] *= inv;
+    for (int c = threadIdx.x; c < L.cols; c += blockDim.x) {
+        const float nv = L.v[c] * inv;
+        L.v[c] = nv;
+        if (L.v_snap) L.v_snap[c] = nv;                  // copy for this forward's backward (the buffer moves on)
+    }
 }
 
 // B1: s[row] = W[row,:] . v     (one CTA per row, 128-bit loads where the row is 16-byte aligned)
@@ -104,10 +108,16 @@ sn_u_sigma_kernel(const __grid_constant__ SnTable tab, const float *__restrict__
     const float tot = ipr_block_sum(acc, red);
     if (update) {
         const float inv = 1.0f / fmaxf(sqrtf(tot), eps);
-        for (int r = threadIdx.x; r < L.rows; r += blockDim.x) L.u[r] = scratch[L.scratch_off + r] * inv;
+        for (int r = threadIdx.x; r < L.rows; r += blockDim.x) {
+            const float nu = scratch[L.scratch_off + r] * inv;
+            L.u[r] = nu;
+            if (L.u_snap) L.u_snap[r] = nu;
+        }
         if (threadIdx.x == 0) *L.sigma = tot * inv;          // u . s = ||s||^2 / max(||s||, eps)
-    } else if (threadIdx.x == 0) {
-        *L.sigma = tot;
+    } else {
+        if (L.u_snap) for (int r = threadIdx.x; r < L.rows; r += blockDim.x) L.u_snap[r] = L.u[r];
+        if (L.v_snap) for (int c = threadIdx.x; c < L.cols; c += blockDim.x) L.v_snap[c] = L.v[c];
+        if (threadIdx.x == 0) *L.sigma = tot;
     }
 }
 

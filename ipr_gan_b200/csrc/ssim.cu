@@ -589,7 +589,8 @@ ssim32_warp_kernel(const SsimParams p)
 
 // loss = 1 - (sum of all partials) / count        (single CTA, fixed order)
 __global__ void __launch_bounds__(1024)
-ssim_finalize_loss_kernel(const float *__restrict__ partial, long long n, float inv_count, float *__restrict__ loss)
+ssim_finalize_loss_kernel(const float *__restrict__ partial, long long n, float inv_count, float loss_scale,
+                          float *__restrict__ loss)
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
@@ -597,7 +598,7 @@ ssim_finalize_loss_kernel(const float *__restrict__ partial, long long n, float 
     float acc = 0.f;
     for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
     const float tot = ipr_block_sum(acc, red);
-    if (threadIdx.x == 0) *loss = 1.0f - tot * inv_count;
+    if (threadIdx.x == 0) *loss = (1.0f - tot * inv_count) * loss_scale;
 }
 
 // out[n] = (sum over the sample's C planes and tiles) / (C*Hv*Wv)
@@ -718,7 +719,7 @@ extern "C" size_t ipr_ssim_workspace_bytes(int64_t batch, int channels, int heig
 extern "C" int ipr_ssim_fwd_bwd_f32(const float *x, const float *y, float *dx, float *loss,
                                     void *workspace, size_t workspace_bytes,
                                     int64_t batch, int channels, int height, int width,
-                                    int normalized, float grad_scale, ipr_stream_t stream)
+                                    int normalized, float grad_scale, float loss_scale, ipr_stream_t stream)
 {
     int rc = check_common(x, y, batch, channels, height, width);
     if (rc != IPR_OK) return rc;
@@ -735,7 +736,7 @@ extern "C" int ipr_ssim_fwd_bwd_f32(const float *x, const float *y, float *dx, f
     rc = dx ? launch_tiles<true>(p, pl, ipr_cu(stream)) : launch_tiles<false>(p, pl, ipr_cu(stream));
     if (rc != IPR_OK) return rc;
     const long long n = p.planes * pl.tiles_r * pl.tiles_c;
-    IPR_LAUNCH_PDL((ssim_finalize_loss_kernel), 1, 1024, 0, ipr_cu(stream), p.partial, n, (float)(1.0 / count), loss);
+    IPR_LAUNCH_PDL((ssim_finalize_loss_kernel), 1, 1024, 0, ipr_cu(stream), p.partial, n, (float)(1.0 / count), loss_scale, loss);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

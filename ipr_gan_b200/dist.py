@@ -35,6 +35,14 @@ def allreduce_mean_(flat_tensor):
     return flat_tensor
 
 
+def allreduce_sum_(flat_tensor):
+    """In-place SUM over ranks (the 1/world factor is folded into the consumer: ``ipr_adam_flat_f32(grad_scale)``
+    for gradients, the host-side division in ``get_metrics`` for the loss slots).  No-op for a single process."""
+    if world() > 1:
+        dist.all_reduce(flat_tensor)
+    return flat_tensor
+
+
 def reduce_metrics(metrics):
     """Average a metrics dict over ranks with one small all-reduce (per-rank means of equal-size shards)."""
     w = world()

@@ -35,12 +35,43 @@ class BlackBoxWrapper(Wrapper):
         self._modules["fn_inp"] = self.fn_inp
         self._modules["fn_out"] = self.fn_out
 
+    def _fused(self):
+        """The inner model's metrics board when the whole generator step runs on the fused path (native DCGAN
+        networks + SSIM watermark loss); None otherwise (`board` falls through the wrappers, None when absent)."""
+        board = self.board
+        return board if board is not None and self.config.loss_fn == "ssim" else None
+
     def compute_g_loss(self):
         self.LossG = self.model.LossG
+        board = self._fused()
+        if board is not None:
+            if self.inhibit:
+                board.slot(board.P_WM).zero_()
+            else:
+                # forward + backward of the SSIM loss in one launch: the scalar goes to its board slot, lambda * dLoss/dx
+                # becomes the seed gradient of the trigger pass (no autograd node, no multiply by grad_output)
+                from ipr_gan_b200 import ops
+                _, dx = ops.ssim_loss_fwd_bwd(self.Gxwm.detach(), self.ywm, self.config.normalized, grad_scale=self.Lambda,
+                                              loss_out=board.slot(board.P_WM), loss_scale=board.loss_scale)
+                self.g_seeds.append((self.Gxwm, dx))
+            self.LossW = board.scalar(board.P_WM)
+            return
         if self.inhibit:
             self.LossW = torch.zeros_like(self.LossG)
         else:
             self.LossW = self.loss_fn(self.Gxwm, self.ywm)
+
+    def _triggers(self, source, produced):
+        """xwm = fn_inp(source), ywm = fn_out(produced) (models/wrappers.py:48-51).  The protected-DCGAN pairing --
+        TransformDist on the latents, a pasted patch on the images -- is ONE launch that reads each tensor once."""
+        import tools
+        from tools.triggers import _PatchTrigger
+        f_in, f_out = self.fn_inp.module, self.fn_out.module
+        if isinstance(f_in, tools.TransformDist) and isinstance(f_out, _PatchTrigger) and produced.is_cuda:
+            from ipr_gan_b200 import ops
+            z = source.detach().to(produced.device, torch.float32, non_blocking=True)
+            return ops.trigger_pair(produced.detach(), f_out.fg, f_out.bg, f_out.position, f_out.config.size, z)
+        return self.fn_inp(source.detach()), self.fn_out(produced.detach())
 
     def forward_g(self, data):
         self.inhibit = data.get("inhibit_bbox", False)
@@ -60,8 +91,7 @@ class BlackBoxWrapper(Wrapper):
             aux.wait_event(fork)
             with torch.cuda.stream(aux):
                 with torch.no_grad():
-                    self.xwm = self.fn_inp(source.detach())
-                    self.ywm = self.fn_out(produced.detach())
+                    self.xwm, self.ywm = self._triggers(source, produced)
                 with DisableBatchNormStats(net):
                     self.Gxwm = net(self.xwm)
             main.wait_stream(aux)
@@ -69,15 +99,15 @@ class BlackBoxWrapper(Wrapper):
                 t.record_stream(main)
             return
         with torch.no_grad():
-            self.xwm = self.fn_inp(source.detach())
-            self.ywm = self.fn_out(produced.detach())
+            self.xwm, self.ywm = self._triggers(source, produced)
         with DisableBatchNormStats(net):
             self.Gxwm = net(self.xwm)
 
     def get_metrics(self):
         metrics = self.model.get_metrics()
         if not self.inhibit:
-            w = self.LossW.item()
+            board = self._fused()
+            w = board.fetch()[board.P_WM] if board is not None else self.LossW.item()
             metrics[f"P/{self.config.loss_fn.upper()}"] = w
             metrics["G/Sum"] += self.Lambda * w
         return metrics
@@ -89,8 +119,17 @@ class BlackBoxWrapper(Wrapper):
         dev = self.device[0]
         concurrent = self._concurrent
         if dev.type == "cuda" and concurrent is not None and concurrent():
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(dev))
+            root = self
+            while isinstance(root, Wrapper):
+                root = root.model
+            # recorded by the inner model just before its optD.step(); valid for ONE generator step (a second
+            # update_g without a new update_d must see the generator weights the first one wrote)
+            ev = getattr(root, "pre_step_event", None)
+            if ev is not None:
+                root.pre_step_event = None
+            else:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
             self._fork_event = ev
 
     def update_g(self, data, update=True):
@@ -99,9 +138,37 @@ class BlackBoxWrapper(Wrapper):
         self.forward_g(data)
         self.compute_g_loss()
         if update:
-            self.model.optG.zero_grad()
-            (self.LossG + self.Lambda * self.LossW).backward()
-            self.model.optG.step()
+            _backward_and_step(self, lambda: self.LossG + self.Lambda * self.LossW)
+
+
+def _backward_and_step(wrapper, total):
+    """optG.zero_grad(); total.backward(); optG.step() (models/wrappers.py:70-74, 121-125).  On the fused path the
+    backward starts from the seed gradients the loss launches produced (`backward_g` of the innermost model)."""
+    backward_g = wrapper.backward_g               # falls through to the wrapped model; None for other model types
+    if backward_g is not None:
+        backward_g(None if wrapper.board is not None else total())
+    else:
+        wrapper.model.optG.zero_grad()
+        total().backward()
+    wrapper.model.optG.step()
+
+
+class _SignHook(object):
+    """Hands the sign vector of normalisation layer i to that layer's backward kernel exactly once per armed step
+    (engine._GeneratorFn.backward): d(sign loss)/d(gamma) is added inside the BatchNorm backward launch."""
+
+    def __init__(self, loss_model, signs):
+        self.gamma_0, self.signs = loss_model.gamma_0, signs
+        self.armed = [False] * len(signs)
+
+    def arm(self):
+        self.armed = [True] * len(self.signs)
+
+    def __call__(self, i):
+        if not self.armed[i]:
+            return None, 0.0, 0.0
+        self.armed[i] = False
+        return self.signs[i], self.gamma_0, 1.0
 
 
 class WhiteBoxWrapper(Wrapper):
@@ -113,11 +180,27 @@ class WhiteBoxWrapper(Wrapper):
         target = getattr(self.model, self.config.target)
         self.loss_model = tools.SignLossModel(target, self.config).to(self.device[0])
         self._modules["sign"] = self.loss_model
+        self._sign_hook = None
+        import networks
+        if self.board is not None and isinstance(target.module, networks.ConvGenerator):
+            _, signs = self.loss_model._collect(target)
+            self._sign_hook = _SignHook(self.loss_model, signs)
+            object.__setattr__(target.module, "_ipr_sign_hook", self._sign_hook)
 
     def compute_g_loss(self):
         target = getattr(self.model, self.config.target)
         self.LossG = self.model.LossG
-        self.LossS = torch.zeros_like(self.LossG) if self.inhibit else self.loss_model(target)
+        board = self.board if self._sign_hook is not None else None
+        if board is not None:
+            if self.inhibit:
+                board.slot(board.P_SIGN).zero_()
+            else:
+                # value: one launch over all gammas into its board slot; gradient: inside the BatchNorm backward
+                self.loss_model.value_into(target, board.slot(board.P_SIGN), board.loss_scale)
+                self._sign_hook.arm()
+            self.LossS = board.scalar(board.P_SIGN)
+        else:
+            self.LossS = torch.zeros_like(self.LossG) if self.inhibit else self.loss_model(target)
         if hasattr(self.model, "LossW"):
             self.Lambda = self.model.Lambda
             self.LossW = self.model.LossW
@@ -131,7 +214,8 @@ class WhiteBoxWrapper(Wrapper):
     def get_metrics(self):
         metrics = self.model.get_metrics()
         if not self.inhibit:
-            s = self.LossS.item()
+            board = self.board if self._sign_hook is not None else None
+            s = board.fetch()[board.P_SIGN] if board is not None else self.LossS.item()
             metrics["P/SignLoss"] = s
             metrics["G/Sum"] += s
         return metrics
@@ -141,6 +225,4 @@ class WhiteBoxWrapper(Wrapper):
         self.forward_g(data)
         self.compute_g_loss()
         if update:
-            self.model.optG.zero_grad()
-            (self.LossG + self.Lambda * self.LossW + self.LossS).backward()
-            self.model.optG.step()
+            _backward_and_step(self, lambda: self.LossG + self.Lambda * self.LossW + self.LossS)

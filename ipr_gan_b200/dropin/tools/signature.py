@@ -85,6 +85,14 @@ class SignLossModel(nn.Module):
         gammas, signs = self._collect(model)
         return _SignLoss.apply(self.gamma_0, len(gammas), *gammas, *signs)
 
+    def value_into(self, model, slot, scale=1.0):
+        """slot[0] <- scale * sign loss, no gradient output (fused path: d/dgamma is added by the normalisation
+        layers' backward kernels, models/protect.py)."""
+        gammas, signs = self._collect(model)
+        with torch.no_grad():
+            ops.sign_loss_fwd_bwd([g.detach() for g in gammas], signs, self.gamma_0, need_grad=False, loss_out=slot,
+                                  loss_scale=scale)
+
     def compute_ber(self, model):
         gammas, signs = self._collect(model)
         with torch.no_grad():

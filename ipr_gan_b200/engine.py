@@ -27,6 +27,10 @@ from ._lib import check, lib
 
 BN_EPS_DEFAULT = 1e-5
 
+# Test hook: when set to a list, every generator / discriminator forward appends the bf16 activations it stored
+# (NHWC), so a parity test can hand the engine's own ReLU / LeakyReLU masks to the oracle (tests/test_gpu_dcgan.py).
+CAPTURE_ACTS = None
+
 
 def _st():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -67,15 +71,16 @@ def colsum_partials(partial, out=None, accumulate=False, scale=1.0, ncols=None):
     return out
 
 
-def colsum_bf16(x2d, out=None, accumulate=False, scale=1.0):
-    """x2d: [rows][C] bf16 -> out[C] fp32."""
+def colsum_bf16(x2d, out=None, accumulate=False, scale=1.0, out_index=None):
+    """x2d: [rows][C] bf16 -> out[C] fp32 (column c lands at out[out_index[c]] when an int32 index is given;
+    accumulate: False / True / 2 = atomic add)."""
     rows, C = x2d.shape
     if out is None:
         out = torch.empty(C, device=x2d.device, dtype=torch.float32)
     nbytes = lib().ipr_colsum_workspace_bytes(C)
     ws = torch.empty(nbytes // 4, device=x2d.device, dtype=torch.float32)
-    check(lib().ipr_colsum_bf16(_p(x2d), rows, C, _p(out), int(bool(accumulate)), float(scale), _p(ws), nbytes, _st()),
-          "ipr_colsum_bf16")
+    check(lib().ipr_colsum_bf16(_p(x2d), rows, C, _p(out), int(accumulate), float(scale), _p(out_index), _p(ws), nbytes,
+                                _st()), "ipr_colsum_bf16")
     return out
 
 
@@ -113,7 +118,7 @@ def bn_relu_bwd(dy, xraw, scale, shift, gamma, mean, rstd, dgamma, dbeta, accumu
     ws = torch.empty(nbytes // 4, device=dy.device, dtype=torch.float32)
     dx = torch.empty_like(dy)
     check(lib().ipr_bn_relu_bwd_bf16(_p(dy), _p(xraw), _p(scale), _p(shift), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgamma),
-                                     _p(dbeta), int(bool(accumulate)), _p(sign), float(gamma0), float(sign_scale),
+                                     _p(dbeta), int(accumulate), _p(sign), float(gamma0), float(sign_scale),
                                      _p(ws), nbytes, dy.numel() // C, C, _st()), "ipr_bn_relu_bwd_bf16")
     return dx
 
@@ -125,11 +130,14 @@ def dfc_fwd(a, w, sigma, bias):
     return logits
 
 
-def dfc_bwd(a, w, sigma, dlogit, want_dw, slope):
+def dfc_bwd(a, w, sigma, dlogit, want_dw, slope, dw_index=None, dbias=None):
+    """-> (da, dw).  dw_index (int32) scatters dw from the activation's feature order into the parameter's own order;
+    dbias (a 1-element fp32 view) receives += sum(dlogit)."""
     B, K = a.shape
     da = torch.empty_like(a)
     dw = torch.empty(K, device=a.device, dtype=torch.float32) if want_dw else None
-    check(lib().ipr_dfc_bwd_bf16(_p(a), _p(w), _p(sigma), _p(dlogit), _p(da), _p(dw), 0, float(slope), B, K, _st()),
+    check(lib().ipr_dfc_bwd_bf16(_p(a), _p(w), _p(sigma), _p(dlogit), _p(da), _p(dw), 0, float(slope), B, K,
+                                 _p(dw_index) if want_dw else None, _p(dbias) if want_dw else None, _st()),
           "ipr_dfc_bwd_bf16")
     return da, dw
 
@@ -152,9 +160,21 @@ class PackSet(object):
     """Every bf16 GEMM operand layout of one network, rebuilt from the network's fp32 parameter arena by ONE
     gather launch (csrc/optim.cu) whenever the masters changed."""
 
-    def __init__(self, module, specs):
+    def __init__(self, module, specs, specs_f32=()):
         self.arena = flat.arena_for(list(module.parameters()))
         dev = self.arena.param.device
+        # fp32 side table: permuted fp32 copies (Linear bias in NHWC feature order, the final GEMV row), same launch
+        parts32, self.slices32, off32 = [], {}, 0
+        for key, param, layout_fn in specs_f32:
+            o = self.arena.offset_of(param)
+            src = (torch.arange(param.numel(), dtype=torch.float64) + o).view(param.shape)
+            idx = layout_fn(src).reshape(-1).to(torch.int32)
+            pad = (-idx.numel()) % 4
+            self.slices32[key] = (off32, idx.numel())
+            parts32.append(torch.cat([idx, torch.full((pad,), -1, dtype=torch.int32)]) if pad else idx)
+            off32 += idx.numel() + pad
+        self.index32 = torch.cat(parts32).to(dev) if parts32 else None
+        self.buf32 = torch.empty(off32, device=dev, dtype=torch.float32) if parts32 else None
         parts, self.slices, off = [], {}, 0
         for key, param, layout_fn in specs:
             o = self.arena.offset_of(param)
@@ -182,7 +202,9 @@ class PackSet(object):
         stamp = (self.arena.version, self.arena.param._version) + tuple(p._version for p in self.arena.params)
         cur = torch.cuda.current_stream(self.buf.device)
         if stamp != self.stamp:
-            check(lib().ipr_gather_pack_bf16(_p(self.arena.param), _p(self.index), _p(self.buf), self.buf.numel(), _st()),
+            check(lib().ipr_gather_pack_bf16(_p(self.arena.param), _p(self.index), _p(self.buf), self.buf.numel(),
+                                             _p(self.index32), _p(self.buf32),
+                                             self.buf32.numel() if self.buf32 is not None else 0, _st()),
                   "ipr_gather_pack_bf16")
             self.stamp = stamp
             self.event = _ev_record(cur)            # other streams (concurrent D(real) / D(fake) passes) wait for the pack
@@ -193,6 +215,11 @@ class PackSet(object):
         self.refresh()
         off, n, shape = self.slices[key]
         return self.buf[off:off + n].view(shape)
+
+    def get32(self, key):
+        self.refresh()
+        off, n = self.slices32[key]
+        return self.buf32[off:off + n]
 
     def clear(self):
         self.stamp = None
@@ -282,13 +309,14 @@ class GenPlans(object):
             specs.append(("ct%d_dg" % i, cv[i][0].weight, self.ct_dg[i].pack_layout))
         specs.append(("ct3", cv[3].weight, _tap27_rows_layout))
         specs.append(("ct3_dg", cv[3].weight, _patch27_layout))
-        self.packs = PackSet(module, specs)
+        self.packs = PackSet(module, specs, [("fcb", module.fc[0].bias, lambda b: b[perm])])
         _ALL_PACKS.append(self.packs)
 
     def perm_on(self, device):
+        """int32 table: NHWC feature n' -> reference feature (scatter index of the kernels)"""
         key = str(device)
         if key not in self._perm_dev:
-            self._perm_dev[key] = self.perm.to(device)
+            self._perm_dev[key] = self.perm.to(device=device, dtype=torch.int32)
         return self._perm_dev[key]
 
 
@@ -318,7 +346,8 @@ class DisPlans(object):
         for i in range(6):
             pk.append(("c%d" % (i + 1), layers[i + 1].weight_orig, self.conv[i].pack_layout))
             pk.append(("c%d_dg" % (i + 1), layers[i + 1].weight_orig, self.conv_dg[i].pack_layout))
-        self.packs = PackSet(module, pk)
+        dperm = self.perm
+        self.packs = PackSet(module, pk, [("w8", layers[7].weight_orig, lambda w: w.reshape(-1)[dperm])])
         _ALL_PACKS.append(self.packs)
         # power-iteration vectors of all layers in ONE buffer (the module's weight_u / weight_v become views), so a
         # forward snapshots them with a single copy; per-layer scratch slices for the batched SN kernels
@@ -351,12 +380,15 @@ class DisPlans(object):
     def perm_on(self, device):
         key = str(device)
         if key not in self._perm_dev:
-            self._perm_dev[key] = self.perm.to(device)
+            self._perm_dev[key] = self.perm.to(device=device, dtype=torch.int32)
         return self._perm_dev[key]
 
-    def sn_table(self, layers, uv, sigma, grads=None, grad_outs=None):
+    def sn_table(self, layers, uv, sigma, grads=None, grad_outs=None, snap=None):
         arr = (SnLayer * 8)()
         for i, l in enumerate(layers):
+            if snap is not None:
+                arr[i].u_snap = snap.data_ptr() + 4 * self.uv_off[i][0]
+                arr[i].v_snap = snap.data_ptr() + 4 * self.uv_off[i][1]
             arr[i].grad_out = grad_outs[i].data_ptr() if grad_outs is not None and grad_outs[i] is not None else None
             arr[i].w = l.weight_orig.data_ptr()
             arr[i].u = uv.data_ptr() + 4 * self.uv_off[i][0]
@@ -418,6 +450,13 @@ def _grad_dst(param):
     return t, False, t
 
 
+def _mark_dirty(module):
+    """A backward pass wrote into the network's gradient arena: the next optimizer.zero_grad() has work to do."""
+    a = flat.arena_of(next(module.parameters()))
+    if a is not None:
+        a.clean = False
+
+
 def _plans(module, cls):
     p = getattr(module, "_ipr_plans", None)
     if p is not None:
@@ -442,9 +481,7 @@ class _GeneratorFn(torch.autograd.Function):
         mg = P.mg
         bns = [module.convs[i][1] for i in range(3)]
         a0 = z.detach().to(torch.bfloat16).contiguous().view(B, 1, 1, -1)
-        perm = P.perm_on(z.device)
-        fcb = fc_b.detach()[perm]
-        h, _ = P.fc.run(a0, P.packs.get("fc"), epi=dense.EPI_BIAS_LRELU, slope=0.0, bias=fcb)
+        h, _ = P.fc.run(a0, P.packs.get("fc"), epi=dense.EPI_BIAS_LRELU, slope=0.0, bias=P.packs.get32("fcb"))
         acts = [h.view(B, mg, mg, 512)]
         raws, means, rstds, scales, shifts = [], [], [], [], []
         ctx.eval_stats = False
@@ -473,6 +510,8 @@ class _GeneratorFn(torch.autograd.Function):
             shifts.append(shift)
         t9, _ = P.last.run(acts[-1], P.packs.get("ct3"), epi=dense.EPI_LINEAR_F32, n_valid=32)
         out = col2im3(t9, True)
+        if CAPTURE_ACTS is not None:
+            CAPTURE_ACTS.append(("G", list(acts)))
         ctx.module = module
         ctx.save_for_backward(a0, out, fc_w, w1, w2, w3, w4, g1, g2, g3, *acts, *raws, *means, *rstds, *scales, *shifts)
         return out
@@ -508,15 +547,14 @@ class _GeneratorFn(torch.autograd.Function):
                 acc_g = False
             sg, g0, sc = (None, 0.0, 0.0)
             if sign_hook is not None:
+                # white-box sign loss (tools/sign_model.py:42-49): d/dgamma rides in this layer's BatchNorm backward.
+                # The hook hands each layer's sign vector out ONCE per armed step, so of the two generator passes
+                # (G(z), G(trigger)) exactly one adds it.
                 sg, g0, sc = sign_hook(i)
-            if acc_g and concurrent_passes():
-                # two generator passes (G(z), G(trigger)) may backpropagate on different streams: every accumulation
-                # into the gradient arena goes through the shared side stream, so gamma/beta gradients take a detour
-                tg, tb = torch.empty_like(gammas[i]), torch.empty_like(gammas[i])
-                dx = bn_relu_bwd(d_act, raws[i], scales[i], shifts[i], gammas[i], means[i], rstds[i], tg, tb, False, sg, g0, sc)
-                fork.run(lambda dg_t=dg_t, db_t=db_t, tg=tg, tb=tb: (dg_t.add_(tg), db_t.add_(tb)), tg, tb)
-            else:
-                dx = bn_relu_bwd(d_act, raws[i], scales[i], shifts[i], gammas[i], means[i], rstds[i], dg_t, db_t, acc_g, sg, g0, sc)
+            # two generator passes may backpropagate on different streams: gamma / beta gradients are added
+            # atomically (two contributions onto a zeroed slot: order-independent, hence still deterministic)
+            dx = bn_relu_bwd(d_act, raws[i], scales[i], shifts[i], gammas[i], means[i], rstds[i], dg_t, db_t,
+                             2 if acc_g else 0, sg, g0, sc)
             dw_t, acc_w, dws[i] = _grad_dst(mod_c[i][0].weight)
             fork.run(lambda i=i, dx=dx, dw_t=dw_t, acc_w=acc_w: P.ct_wg[i].run(dx, acts[i], dw_t, accumulate=acc_w), dx, dw_t)
             wd = P.packs.get("ct%d_dg" % i)
@@ -528,9 +566,10 @@ class _GeneratorFn(torch.autograd.Function):
         dfc_t, acc_fc, dfc_w = _grad_dst(module.fc[0].weight)
         fork.run(lambda: P.fc_wg.run(dh, a0, dfc_t, accumulate=acc_fc), dh, dfc_t)
         perm = P.perm_on(dev)
-        dfc_b = torch.empty(fc_w.shape[0], device=dev, dtype=torch.float32)
-        dfc_b[perm] = colsum_bf16(dh.view(B, -1))
+        db_t, acc_fb, dfc_b = _grad_dst(module.fc[0].bias)
+        colsum_bf16(dh.view(B, -1), out=db_t, accumulate=2 if acc_fb else 0, out_index=perm)
         fork.join()
+        _mark_dirty(module)
         return (None, None, dfc_w, dfc_b, dws[0], dgs[0], dbs[0], dws[1], dgs[1], dbs[1], dws[2], dgs[2], dbs[2], ret4)
 
 
@@ -563,9 +602,9 @@ class _DiscriminatorFn(torch.autograd.Function):
         scratch = torch.empty(P.scratch_floats, device=dev, dtype=torch.float32)
         cur = torch.cuda.current_stream(dev)
         _ev_wait(_SN_EVENTS.get(id(P)), cur)       # a pass on another stream advanced u/v: keep the reference's order
-        check(lib().ipr_sn_power_iter_f32(P.sn_table(layers, P.uv, sigma), 8, int(module.training), 1e-12,
+        uv = torch.empty_like(P.uv)                # this forward's copy of u / v, written by the same kernels
+        check(lib().ipr_sn_power_iter_f32(P.sn_table(layers, P.uv, sigma, snap=uv), 8, int(module.training), 1e-12,
                                           _p(scratch), _st()), "ipr_sn_power_iter_f32")
-        uv = P.uv.clone()
         _SN_EVENTS[id(P)] = _ev_record(cur)
         sig = [sigma[i:i + 1] for i in range(8)]
         # D(fake.detach()) and D(generated) see the same image in one step: the model hands the patch matrix over on
@@ -585,9 +624,10 @@ class _DiscriminatorFn(torch.autograd.Function):
             a, _ = plan.run(acts[-1], P.packs.get("c%d" % (i + 1)), epi=dense.EPI_BIAS_LRELU, slope=0.1, sigma=sig[i + 1],
                             bias=bs[i + 1].detach())
             acts.append(a)
-        perm = P.perm_on(dev)
-        w8 = ws[7].detach().reshape(-1)[perm]
+        w8 = P.packs.get32("w8")
         logits = dfc_fwd(acts[-1].view(B, -1), w8, sig[7], bs[7].detach())
+        if CAPTURE_ACTS is not None:
+            CAPTURE_ACTS.append(("D", list(acts)))
         ctx.module, ctx.param_grads = module, param_grads
         ctx.x_needs_grad = x.requires_grad
         ctx.save_for_backward(col, w8, sigma, uv, *ws, *acts)
@@ -609,13 +649,14 @@ class _DiscriminatorFn(torch.autograd.Function):
         gW, gB = [None] * 8, [None] * 8
         gW_ret = {}
         a7 = acts[-1].view(B, -1)
-        dy, dw8 = dfc_bwd(a7, w8, sig[7], dlogits, want, 0.1)
+        db8 = None
         if want:
-            perm = P.perm_on(dev)
-            g8 = torch.empty_like(dw8)
-            g8[perm] = dw8
-            gW[7] = g8.view(1, -1)
-            gB[7] = dlogits.sum().view(1)
+            db8, acc8, gB[7] = _grad_dst(layers[7].bias)
+            if not acc8:
+                db8.zero_()
+        dy, dw8 = dfc_bwd(a7, w8, sig[7], dlogits, want, 0.1, dw_index=P.perm_on(dev), dbias=db8)
+        if want:
+            gW[7] = dw8.view(1, -1)
         dy = dy.view(acts[-1].shape)
         fork = _Fork(dev)
         if want:
@@ -657,6 +698,7 @@ class _DiscriminatorFn(torch.autograd.Function):
                 return scratch
             keep = fork.run(_sn_grad, *[g for g in gW if g is not None])
             fork.join()
+            _mark_dirty(module)
         grads = []
         for i in range(8):
             grads += [gW_ret[i] if (want and i in gW_ret) else gW[i], gB[i]]

@@ -26,6 +26,9 @@ class Arena(object):
         self.param = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.version = 0                                          # bumped by whoever rewrites the masters
+        self.clean = True                                         # gradient arena known to be all zeros
+        self.slots = None                                         # 4 floats riding behind/before the gradients
+        self.reduce_view = self.grad                              # what a data-parallel all-reduce covers
         with torch.no_grad():
             for p, o in zip(params, self.offsets):
                 n = p.numel()
@@ -49,8 +52,33 @@ class Arena(object):
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
 
     def zero_grad(self):
-        self.grad.zero_()
+        if not self.clean:                  # FlatAdam clears the arena as it consumes it: usually nothing to do
+            self.grad.zero_()
+            self.clean = True
         self.bind_grads()
+
+    def _rebind(self, grad):
+        with torch.no_grad():
+            grad.copy_(self.grad)
+        self.grad = grad
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+def share_gradient_buffer(first, second):
+    """Lay two networks' gradient arenas out as ONE allocation  [first.grad | first.slots | second.slots | second.grad].
+
+    Each network's data-parallel all-reduce then covers its gradients AND its four metric slots in a single
+    contiguous call (the per-rank loss sums ride along, as SURVEY.md 8e asks), and the eight slots together form
+    one contiguous "board" that ``get_metrics()`` fetches with a single copy.  -> the board view."""
+    dev = first.grad.device
+    n1, n2 = first.numel, second.numel
+    buf = torch.zeros(n1 + 8 + n2, device=dev, dtype=torch.float32)
+    first._rebind(buf[:n1])
+    second._rebind(buf[n1 + 8:])
+    first.slots, second.slots = buf[n1:n1 + 4], buf[n1 + 4:n1 + 8]
+    first.reduce_view, second.reduce_view = buf[:n1 + 4], buf[n1 + 4:]
+    return buf[n1:n1 + 8]
 
 
 def arena_for(params):

@@ -112,18 +112,19 @@ def _ssim_ws(x):
     return torch.empty(max(1, (nbytes + 3) // 4), device=x.device, dtype=torch.float32), nbytes
 
 
-def ssim_loss_fwd_bwd(x, y, normalized, grad_scale=1.0, need_grad=True):
-    """-> (loss 0-dim, dx or None):  loss = 1 - SSIM,  dx = grad_scale * dloss/dx."""
+def ssim_loss_fwd_bwd(x, y, normalized, grad_scale=1.0, need_grad=True, loss_out=None, loss_scale=1.0):
+    """-> (loss 0-dim, dx or None):  loss = 1 - SSIM,  dx = grad_scale * dloss/dx.  ``loss_out``: an existing
+    1-element fp32 CUDA view to write the loss into (a metrics slot)."""
     x = _req(x, "x")
     y = _req(y, "y")
     if x.shape != y.shape or x.dim() != 4:
         raise IprError("ssim: x and y must be (N, C, H, W) tensors of the same shape")
     B, C, H, W = x.shape
     ws, nbytes = _ssim_ws(x)
-    loss = torch.empty((), device=x.device, dtype=torch.float32)
+    loss = torch.empty((), device=x.device, dtype=torch.float32) if loss_out is None else loss_out
     dx = torch.empty_like(x) if need_grad else None
     check(lib().ipr_ssim_fwd_bwd_f32(_p(x), _p(y), _p(dx) if need_grad else None, _p(loss), _p(ws), nbytes,
-                                     B, C, H, W, int(bool(normalized)), float(grad_scale), _stream()),
+                                     B, C, H, W, int(bool(normalized)), float(grad_scale), float(loss_scale), _stream()),
           "ipr_ssim_fwd_bwd_f32")
     return loss, dx
 
@@ -163,20 +164,25 @@ def _sign_table(gammas, signs, grads):
     return arr, keep
 
 
-def sign_loss_fwd_bwd(gammas, signs, gamma_0, grad_scale=1.0, grads=None, accumulate=False):
-    """-> (loss 0-dim, grads list).  ``grads`` (optional) are destinations to write / accumulate into."""
-    if grads is None:
+def sign_loss_fwd_bwd(gammas, signs, gamma_0, grad_scale=1.0, grads=None, accumulate=False, need_grad=True,
+                      loss_out=None, loss_scale=1.0):
+    """-> (loss 0-dim, grads list).  ``grads`` (optional) are destinations to write / accumulate into;
+    ``need_grad=False`` evaluates the loss only (its gradient then rides in the normalisation layers' backward);
+    ``loss_out``: an existing 1-element view to write the loss into (single-call signatures only)."""
+    if grads is None and need_grad:
         grads = [torch.empty_like(g) for g in gammas]
     total = 0
     loss = torch.empty((), device=gammas[0].device, dtype=torch.float32)
+    if loss_out is not None and len(gammas) <= _lib.SIGN_MAX_LAYERS:
+        loss = loss_out
     part = loss
     for lo in range(0, len(gammas), _lib.SIGN_MAX_LAYERS):
         hi = lo + _lib.SIGN_MAX_LAYERS
-        arr, _keep = _sign_table(gammas[lo:hi], signs[lo:hi], grads[lo:hi])
+        arr, _keep = _sign_table(gammas[lo:hi], signs[lo:hi], grads[lo:hi] if grads is not None else None)
         if lo > 0:
-            part = torch.empty_like(loss)
+            part = torch.empty((), device=gammas[0].device, dtype=torch.float32)
         check(lib().ipr_sign_loss_fwd_bwd_f32(arr, len(arr), float(gamma_0), float(grad_scale),
-                                              int(bool(accumulate)), _p(part), _stream()),
+                                              int(bool(accumulate)), float(loss_scale), _p(part), _stream()),
               "ipr_sign_loss_fwd_bwd_f32")
         total = part if lo == 0 else total + part
     return total, grads
@@ -193,6 +199,44 @@ def sign_ber_counts(gammas, signs):
         check(lib().ipr_sign_ber_i32(arr, len(arr), _p(part), _stream()), "ipr_sign_ber_i32")
         out = out + part
     return out
+
+
+# ------------------------------------------------------------------------------ step scalars
+def hinge_d_loss(real_logits, fake_logits, slots, loss_scale=1.0):
+    """models/dcgan.py:31-35 in one launch: slots[0:3] <- (LossD, LossR, LossF); -> (dLossD/dreal, dLossD/dfake)."""
+    r = _req(real_logits, "real_logits")
+    f = _req(fake_logits, "fake_logits")
+    if r.numel() != f.numel():
+        raise IprError("hinge loss: real / fake batch mismatch")
+    dr, df = torch.empty_like(r), torch.empty_like(f)
+    check(lib().ipr_hinge_d_loss_f32(_p(r), _p(f), r.numel(), float(loss_scale), _p(slots), _p(dr), _p(df), _stream()),
+          "ipr_hinge_d_loss_f32")
+    return dr, df
+
+
+def gen_adv_loss(logits, slot, loss_scale=1.0):
+    """models/dcgan.py:37-40: slot[0] <- -mean(logits); -> d/dlogits (= -1/B)."""
+    l = _req(logits, "logits")
+    d = torch.empty_like(l)
+    check(lib().ipr_gen_adv_loss_f32(_p(l), l.numel(), float(loss_scale), _p(slot), _p(d), _stream()),
+          "ipr_gen_adv_loss_f32")
+    return d
+
+
+class DeviceNormal(object):
+    """Standard-normal draws made on the device (Philox4x32-10 keyed by ``seed``; the stream position lives in
+    device memory and advances with every launch, so a captured CUDA graph draws fresh latents on every replay)."""
+
+    def __init__(self, device, seed):
+        self.seed = int(seed) & ((1 << 64) - 1)
+        self.counter = torch.zeros(1, device=device, dtype=torch.int64)
+        self.ticket = torch.zeros(1, device=device, dtype=torch.int32)
+
+    def fill_(self, out):
+        out = _req(out, "out")
+        check(lib().ipr_randn_f32(_p(out), out.numel(), self.seed, _p(self.counter), _p(self.ticket), _stream()),
+              "ipr_randn_f32")
+        return out
 
 
 # ------------------------------------------------------------------------------ verification

@@ -2,9 +2,10 @@
 (csrc/optim.cu).  It IS a ``torch.optim.Adam`` (same ``param_groups`` / ``state_dict`` format, so checkpoints
 written by the reference load and vice versa), only the arithmetic moved.
 
-With ``torch.distributed`` initialised (one process per GPU) ``step()`` first all-reduces the gradient arena over
-NCCL -- one call per network per step -- and divides by the world size: the reference's ``nn.DataParallel``
-gradient reduction (experiments/base.py:36-39) without the per-forward parameter broadcast.
+With ``torch.distributed`` initialised (one process per GPU) ``step()`` first all-reduces (sum) the gradient arena over
+NCCL -- one call per network per step, carrying the step's loss slots along -- and the Adam launch applies the
+1/world factor: the reference's ``nn.DataParallel`` gradient reduction (experiments/base.py:36-39) without the
+per-forward parameter broadcast.
 """
 import ctypes
 
@@ -34,6 +35,7 @@ class FlatAdam(torch.optim.Adam):
         self._m = torch.zeros_like(self.arena.param)
         self._v = torch.zeros_like(self.arena.param)
         self._step = torch.zeros((), device=dev, dtype=torch.float32)
+        self._ticket = torch.zeros(1, device=dev, dtype=torch.int32)
         self._bind_state()
 
     def _bind_state(self):
@@ -82,12 +84,16 @@ class FlatAdam(torch.optim.Adam):
             raise RuntimeError("FlatAdam: the parameters were moved out of their arena (module.to() / a new p.data "
                                "after the optimizer was built); rebuild the optimizer")
         arena.bind_grads()
-        dist.allreduce_mean_(arena.grad)            # no-op for a single process
+        # ONE summing all-reduce per network per step over [gradients | metric slots] (no-op for a single process);
+        # the mean's 1/world is folded into the Adam launch, which also clears the arena as it consumes it
+        dist.allreduce_sum_(arena.reduce_view)
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         check(lib().ipr_adam_flat_f32(ctypes.c_void_p(arena.param.data_ptr()), ctypes.c_void_p(arena.grad.data_ptr()),
                                       ctypes.c_void_p(self._m.data_ptr()), ctypes.c_void_p(self._v.data_ptr()),
                                       arena.numel, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
-                                      float(g["eps"]), float(g["weight_decay"]),
-                                      ctypes.c_void_p(self._step.data_ptr()), st), "ipr_adam_flat_f32")
+                                      float(g["eps"]), float(g["weight_decay"]), 1.0 / dist.world(), 1,
+                                      ctypes.c_void_p(self._step.data_ptr()), ctypes.c_void_p(self._ticket.data_ptr()),
+                                      st), "ipr_adam_flat_f32")
         arena.version += 1
+        arena.clean = True
         return loss

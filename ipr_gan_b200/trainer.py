@@ -21,8 +21,10 @@ from ipr_gan_b200 import _lib, engine  # noqa: E402
 
 
 class ProtectedDCGANTrainer(object):
-    def __init__(self, batch, device, seed=1234, fn_inp="TransformDist", use_graph=True, size=32):
+    def __init__(self, batch, device, seed=1234, fn_inp="TransformDist", use_graph=True, size=32,
+                 device_latents=False):
         self.batch, self.device, self.use_graph = batch, device, use_graph
+        self.device_latents = device_latents
         torch.manual_seed(seed)                      # identical initial replicas on every rank
         mcfg = presets.dcgan_model(size)
         if use_graph:
@@ -37,16 +39,23 @@ class ProtectedDCGANTrainer(object):
         self.latent_host = torch.zeros(batch, 128).pin_memory()
         self.graph = None
         self.launches_per_step = None
+        # latents drawn on the device (Philox, position kept in device memory): no host randn + H2D copy per step
+        # (experiments/image_generation.py:93-96); one stream per rank
+        from ipr_gan_b200 import dist, ops
+        self.normal = ops.DeviceNormal(device, seed * 7919 + dist.rank()) if device_latents else None
 
     # one reference-API step on whatever is in the static device buffers
     def _step(self):
+        if self.normal is not None:
+            self.normal.fill_(self.latent)
         self.model.update_d({"real_sample": self.real, "latent": self.latent})
         self.model.update_g({"fake_sample": self.model.fake_sample})
 
     def set_inputs(self, real, latent):
         """Stage a host (or device) batch into the static device buffers (async when the source is pinned)."""
         self.real.copy_(real, non_blocking=True)
-        self.latent.copy_(latent, non_blocking=True)
+        if latent is not None:
+            self.latent.copy_(latent, non_blocking=True)
 
     def capture(self, warmup=3):
         """Warm up eagerly on a side stream, then capture the step into a CUDA graph."""
@@ -74,12 +83,15 @@ class ProtectedDCGANTrainer(object):
         """One training step on the current contents of the device buffers."""
         if self.graph is not None:
             self.graph.replay()
+            board = self.model.board
+            if board is not None:
+                board.touch()                       # the replay rewrote the loss slots behind the host's back
         else:
             self._step()
 
-    def step_from_host(self, real_cpu, latent_cpu):
+    def step_from_host(self, real_cpu, latent_cpu=None):
         """The call a user of the reference makes (experiments/image_generation.py:92-101): host tensors in,
-        metrics dict (Python floats) out."""
+        metrics dict (Python floats) out.  With ``device_latents`` the latent argument is not needed."""
         self.set_inputs(real_cpu, latent_cpu)
         self.step()
         return self.model.get_metrics()

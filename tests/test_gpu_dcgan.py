@@ -16,17 +16,21 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-# Gradients of EARLY layers differ from the pure-fp32 oracle by up to ~10 % in Frobenius norm at random
-# init.  This is not kernel error: storing activations in bf16 flips ~0.5 % of the ReLU masks per layer and
-# every flip changes that element's gradient by 100 % (sqrt(flipped fraction) per layer).  The fp32 PyTorch
-# oracle reproduces the same figure when its activations are rounded to bf16 at the engine's storage points
-# (oracle.gen_forward_sim_bf16 / dis_forward_sim_bf16; numbers in DESIGN.md).  So gradients are held to 2e-2
-# against that bf16-matched oracle, forward results and losses to 2e-2 against the pure fp32 oracle.
-FP32_GRAD_SANITY = 0.25
-# Even against the bf16-matched oracle a few masks still flip (fp32 accumulation order decides some bf16 roundings
-# of values next to zero), so whole-network gradients are held to 8e-2 there; every individual kernel is held to
-# <= 5e-3 on identical inputs in test_gpu_dense.py / test_layer_kernels_exact below.
-MATCHED_GRAD_TOL = 8e-2
+# Whole-network gradients are held to the north_star's bf16 budget (2e-2, relative Frobenius norm per tensor) against
+# the oracle evaluated with the engine's bf16 storage points AND the engine's own ReLU / LeakyReLU on/off pattern
+# (oracle.gen_forward_sim_bf16 / dis_forward_sim_bf16 with ``masks``).  Why the pattern is prescribed: two bf16
+# evaluations of the same network disagree on the sign of a few pre-activations that are ~0 (about 0.5 % per layer at
+# random init); each such flip changes that element's gradient by 100 %, which says nothing about the kernels.  With
+# the pattern fixed, every remaining difference is arithmetic (accumulation order, bf16 rounding of values).
+GRAD_TOL = 2e-2
+
+
+def _nchw_masks(acts, first_view=None):
+    out = []
+    for i, a in enumerate(acts):
+        m = (a.float() > 0).permute(0, 3, 1, 2).contiguous().cpu()
+        out.append(m)
+    return out
 
 
 def _pair(seed=0):
@@ -42,21 +46,25 @@ def _pair(seed=0):
 
 @pytest.mark.parametrize("B", [8, 64, 5, 1])
 def test_generator_forward_backward(B):
+    from ipr_gan_b200 import engine
+    from oracle import ipr_oracle as orc
     G, _, Go, _ = _pair()
     z = torch.randn(B, 128)
-    from oracle import ipr_oracle as orc
     Gs = copy.deepcopy(Go)
-    out = G(z.cuda())
+    engine.CAPTURE_ACTS = []
+    try:
+        out = G(z.cuda())
+        (_, acts), = engine.CAPTURE_ACTS
+    finally:
+        engine.CAPTURE_ACTS = None
     ref = Go(z)
-    sim = orc.gen_forward_sim_bf16(Gs, z)
+    sim = orc.gen_forward_sim_bf16(Gs, z, masks=_nchw_masks(acts))
     assert out.shape == (B, 3, 32, 32) and rel(out, ref) < 2e-2 and rel(out, sim) < 1e-2
     g = torch.randn_like(ref)
     out.backward(g.cuda())
-    ref.backward(g)
     sim.backward(g)
-    for (n, p), (_, q), (_, r) in zip(G.named_parameters(), Go.named_parameters(), Gs.named_parameters()):
-        assert rel(p.grad, r.grad) < MATCHED_GRAD_TOL, (n, rel(p.grad, r.grad))   # bf16-matched oracle
-        assert rel(p.grad, q.grad) < FP32_GRAD_SANITY, (n, rel(p.grad, q.grad))  # pure fp32 oracle (mask flips)
+    for (n, p), (_, r) in zip(G.named_parameters(), Gs.named_parameters()):
+        assert rel(p.grad, r.grad) < GRAD_TOL, (n, rel(p.grad, r.grad))
     for (n, b), (_, c) in zip(G.named_buffers(), Go.named_buffers()):      # running statistics updated alike
         assert rel(b.float(), c.float()) < 2e-2, n
     # eval mode uses the running statistics
@@ -67,30 +75,35 @@ def test_generator_forward_backward(B):
 
 @pytest.mark.parametrize("B", [8, 64, 5, 1])
 def test_discriminator_forward_backward(B):
+    from ipr_gan_b200 import engine
+    from oracle import ipr_oracle as orc
     _, D, _, Do = _pair(1)
     x = torch.randn(B, 3, 32, 32).clamp(-1, 1)
     xg = x.clone().cuda().requires_grad_(True)
     xo = x.clone().requires_grad_(True)
-    from oracle import ipr_oracle as orc
     Ds = copy.deepcopy(Do)
     xs = x.clone().requires_grad_(True)
-    out, ref, sim = D(xg), Do(xo), orc.dis_forward_sim_bf16(Ds, xs)
+    engine.CAPTURE_ACTS = []
+    try:
+        out = D(xg)
+        (_, acts), = engine.CAPTURE_ACTS
+    finally:
+        engine.CAPTURE_ACTS = None
+    ref, sim = Do(xo), orc.dis_forward_sim_bf16(Ds, xs, masks=_nchw_masks(acts))
     assert out.shape == (B,) and rel(out, ref) < 2e-2 and rel(out, sim) < 1e-2
-    loss = torch.relu(1 - out).mean()
-    loss.backward()
-    torch.relu(1 - ref).mean().backward()
-    torch.relu(1 - sim).mean().backward()
-    # LeakyReLU-mask flips are a per-element random effect: with fewer than 8 samples their relative weight grows
-    tol = MATCHED_GRAD_TOL * (1.5 if B < 8 else 1.0)
-    assert rel(xg.grad, xs.grad) < tol and rel(xg.grad, xo.grad) < FP32_GRAD_SANITY
-    for (n, p), (_, q), (_, r) in zip(D.named_parameters(), Do.named_parameters(), Ds.named_parameters()):
-        assert rel(p.grad, r.grad) < tol, (n, rel(p.grad, r.grad))
-        assert rel(p.grad, q.grad) < FP32_GRAD_SANITY, (n, rel(p.grad, q.grad))
+    # a gradient that reaches every logit (the hinge gates most of them off at random init)
+    w = torch.randn(B)
+    (out * w.cuda()).sum().backward()
+    (sim * w).sum().backward()
+    assert rel(xg.grad, xs.grad) < GRAD_TOL, rel(xg.grad, xs.grad)
+    for (n, p), (_, r) in zip(D.named_parameters(), Ds.named_parameters()):
+        assert rel(p.grad, r.grad) < GRAD_TOL, (n, rel(p.grad, r.grad))
     for (n, b), (_, c) in zip(D.named_buffers(), Do.named_buffers()):      # power-iteration state advanced alike
         assert rel(b, c) < 1e-3, n
 
 
-def test_protected_step_vs_oracle(watermark_path):
+@pytest.mark.parametrize("B", [16, 64])                 # 64 = BASELINE config 1 (the reference's own CPU-runnable case)
+def test_protected_step_vs_oracle(watermark_path, B):
     """update_d + update_g through models.DCGAN -> BlackBoxWrapper -> WhiteBoxWrapper (drop-in API) vs the oracle step."""
     import models
     from configs import presets
@@ -104,7 +117,6 @@ def test_protected_step_vs_oracle(watermark_path):
     model = models.WhiteBoxWrapper(model, presets.dcgan_whitebox())
     fg, bg = orc.load_watermark(watermark_path, 16, True, True)
     ref = orc.DCGANStepOracle(Go, Do, orc.transform_dist, lambda y: orc.paste_patch(y, fg, bg, "tl", 16))
-    B = 16
     for step in range(2):
         real, z = orc.synth_step_inputs(B, seed=1234 + step)
         model.update_d({"real_sample": real, "latent": z})
@@ -214,3 +226,92 @@ def test_stream_schedules_are_bit_identical(monkeypatch):
     m1, p1 = run(True, True)
     assert m0 == m1
     assert all(torch.equal(a, b) for a, b in zip(p0, p1))
+
+
+def test_graph_replay_equals_eager():
+    """bench.py times CUDA-graph replays of the step: the captured graph must do exactly what the eager step does --
+    metrics and every parameter bit-identical over three steps with fresh inputs (experiments/image_generation.py:86-101)."""
+    from ipr_gan_b200.trainer import ProtectedDCGANTrainer
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(11)
+    warm = (torch.randn(64, 3, 32, 32, generator=g).clamp(-1, 1), torch.randn(64, 128, generator=g))
+    batches = [(torch.randn(64, 3, 32, 32, generator=g).clamp(-1, 1), torch.randn(64, 128, generator=g)) for _ in range(3)]
+
+    def run(use_graph):
+        tr = ProtectedDCGANTrainer(64, dev, use_graph=use_graph)
+        tr.set_inputs(*warm)
+        tr.capture(warmup=3)                   # three eager warm-up steps on both sides (+ the capture when use_graph)
+        assert (tr.graph is not None) == use_graph
+        out = []
+        for real, z in batches:
+            out.append(tr.step_from_host(real, z))
+        torch.cuda.synchronize()
+        params = [p.detach().clone() for p in list(tr.model.G.parameters()) + list(tr.model.D.parameters())]
+        bufs = [b.detach().clone() for b in list(tr.model.G.buffers()) + list(tr.model.D.buffers())]
+        return out, params, bufs
+
+    m_e, p_e, b_e = run(False)
+    m_g, p_g, b_g = run(True)
+    assert m_e == m_g, (m_e, m_g)
+    assert all(torch.equal(a, b) for a, b in zip(p_e, p_g))
+    assert all(torch.equal(a, b) for a, b in zip(b_e, b_g))
+    assert len({tuple(sorted(m.items())) for m in m_g}) == 3          # the replays really consumed the new inputs
+
+
+def test_trigger_pass_leaves_running_stats_alone():
+    """A7, models/util.py:55-69: inside DisableBatchNormStats the generator normalises with BATCH statistics (it is in
+    training mode) but running_mean / running_var / num_batches_tracked do not move; outside they do."""
+    import networks
+    from models.util import DisableBatchNormStats
+    torch.manual_seed(3)
+    G = networks.ConvGenerator32().cuda().train()
+    z = torch.randn(16, 128, device="cuda")
+    G(z)                                                              # one ordinary forward: statistics now non-trivial
+
+    def snap():
+        return {k: v.detach().clone() for k, v in G.state_dict().items() if "running" in k or "tracked" in k}
+    before = snap()
+    assert len(before) == 9
+    with DisableBatchNormStats(G):
+        y_trig = G(z * 3.0 + 1.0)
+    after = snap()
+    assert all(torch.equal(before[k], after[k]) for k in before)
+    assert all(m.track_running_stats for m in G.modules() if isinstance(m, torch.nn.BatchNorm2d))
+    # it used batch statistics, not the running ones: an eval-mode forward of the same input differs
+    G.eval()
+    with torch.no_grad():
+        y_eval = G(z * 3.0 + 1.0)
+    G.train()
+    assert rel(y_trig, y_eval) > 1e-2
+    G(z)
+    moved = snap()
+    assert all(not torch.equal(before[k], moved[k]) for k in before)
+    assert int(moved["convs.0.1.num_batches_tracked"]) == int(before["convs.0.1.num_batches_tracked"]) + 1
+
+
+def test_packed_weights_follow_the_masters():
+    """The bf16 GEMM operands are rebuilt whenever the fp32 masters change by any route that PyTorch versions:
+    load_state_dict, a stock torch optimizer, an in-place edit of one parameter."""
+    import networks
+    from oracle import ipr_oracle as orc
+    torch.manual_seed(9)
+    G = networks.ConvGenerator32().cuda()
+    Go = orc.make_generator()
+    z = torch.randn(8, 128)
+    G(z.cuda())                                                       # packs built from the initial weights
+    torch.manual_seed(10)
+    other = orc.make_generator().state_dict()
+    G.load_state_dict(other)
+    Go.load_state_dict(other)
+    assert rel(G(z.cuda()), Go(z)) < 2e-2
+    opt, opto = torch.optim.SGD(G.parameters(), lr=0.5), torch.optim.SGD(Go.parameters(), lr=0.5)
+    gsel = torch.randn(8, 3, 32, 32)
+    G(z.cuda()).backward(gsel.cuda())
+    Go(z).backward(gsel)
+    opt.step(), opto.step()
+    assert rel(G(z.cuda()), Go(z)) < 4e-2                              # one SGD step on bf16 vs fp32 gradients
+    with torch.no_grad():
+        G.convs[3].weight[:, 0] = 0.0
+        Go.convs[3].weight[:, 0] = 0.0
+    out = G(z.cuda())
+    assert float(out[:, 0].abs().max()) == 0.0 and rel(out, Go(z)) < 4e-2

@@ -171,3 +171,20 @@ def test_tap_expanded_three_channel_layers(B, H):
     got = engine.col2im3(t9, False)
     want = F.conv_transpose2d(bf(a), bf(wc), stride=1, padding=1) / 2.5
     close(got, want, tol=2e-3)
+
+
+# Batch 512 is the shape bench.py times (BASELINE config 2): every persistent CTA walks many tiles, the TMEM accumulator
+# double-buffers, the TMA ring wraps many times.  The small-batch cases above never reach those code paths.
+@pytest.mark.parametrize("fn,args", [
+    ("test_conv3_forward_bias_lrelu", (512, 64, 128, 16)), ("test_conv3_forward_bias_lrelu", (512, 256, 512, 4)),
+    ("test_conv4s2_forward", (512, 64, 64, 32)), ("test_conv4s2_forward", (512, 256, 256, 8)),
+    ("test_convT4s2_forward_with_stats", (512, 512, 256, 4)), ("test_convT4s2_forward_with_stats", (512, 128, 64, 16)),
+    ("test_data_gradients", ("conv3_dgrad", 512, 128, 64, 16)), ("test_data_gradients", ("conv4s2_dgrad", 512, 64, 64, 16)),
+    ("test_data_gradients", ("convT4s2_dgrad", 512, 128, 256, 16)),
+    ("test_weight_gradients", ("conv3", 512, 64, 128, 16)), ("test_weight_gradients", ("conv4s2", 512, 64, 64, 32)),
+    ("test_weight_gradients", ("convT4s2", 512, 512, 256, 4)), ("test_weight_gradients", ("convT4s2", 512, 128, 64, 16)),
+    ("test_weight_gradients", ("linear", 512, 128, 8192, 1)),
+    ("test_tap_expanded_three_channel_layers", (512, 32)),
+])
+def test_batch_512_shapes(fn, args):
+    globals()[fn](*args)
