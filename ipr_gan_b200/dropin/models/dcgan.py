@@ -75,6 +75,7 @@ class DCGAN(Model):
         if flat_adam and isinstance(self.G.module, networks.ConvGenerator) and \
                 isinstance(self.D.module, networks.SNDiscriminator):
             self.board = MetricsBoard(self.optD.arena, self.optG.arena)
+            self.optD.arena.track_clean = self.optG.arena.track_clean = True
         self.g_seeds = []                # (tensor, gradient) pairs the generator step back-propagates from
 
     # ---- losses (models/dcgan.py:31-40)
@@ -128,8 +129,12 @@ class DCGAN(Model):
 
     def _d_on_fake(self):
         fake = self.fake_sample.detach()
-        self.fake_logits = self.D(fake)
-        col = getattr(fake, "_ipr_col", None)       # patch matrix of the image: update_g's D(generated) reuses it
+        self.D.module._ipr_keep_col = True          # patch matrix of the image: update_g's D(generated) reuses it
+        try:
+            self.fake_logits = self.D(fake)
+        finally:
+            self.D.module._ipr_keep_col = False
+        col = getattr(fake, "_ipr_col", None)
         if col is not None:
             self.fake_sample._ipr_col = col
 

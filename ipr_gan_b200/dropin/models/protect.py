@@ -60,6 +60,8 @@ class BlackBoxWrapper(Wrapper):
             self.LossW = torch.zeros_like(self.LossG)
         else:
             self.LossW = self.loss_fn(self.Gxwm, self.ywm)
+            if self.board is not None:       # fused inner model, other loss (l1 / mse): lambda * dLossW seeds the backward
+                self.g_seeds.append((self.LossW, torch.full_like(self.LossW, float(self.Lambda))))
 
     def _triggers(self, source, produced):
         """xwm = fn_inp(source), ywm = fn_out(produced) (models/wrappers.py:48-51).  The protected-DCGAN pairing --

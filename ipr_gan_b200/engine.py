@@ -607,17 +607,21 @@ class _DiscriminatorFn(torch.autograd.Function):
                                           _p(scratch), _st()), "ipr_sn_power_iter_f32")
         _SN_EVENTS[id(P)] = _ev_record(cur)
         sig = [sigma[i:i + 1] for i in range(8)]
-        # D(fake.detach()) and D(generated) see the same image in one step: the model hands the patch matrix over on
-        # the tensor object itself (dropin/models/dcgan.py), so its lifetime is the image's lifetime
+        # D(fake.detach()) and D(generated) see the same image in one step: when the model asks for it
+        # (``module._ipr_keep_col``, set by dropin/models/dcgan.py around D(fake)) the patch matrix is handed over on the
+        # tensor object itself, so its lifetime is the image's lifetime.  Never stashed implicitly: a persistent input
+        # buffer (the trainer's static ``real`` tensor) would otherwise carry a patch matrix of an OLD batch into a
+        # CUDA-graph capture, where the version check below cannot see the replay-time copies.
         stash = getattr(x, "_ipr_col", None)
         if stash is not None and stash[1] == x._version and stash[0].shape[0] == B and stash[0].device == dev:
             col = stash[0]
         else:
             col = im2col3(x.detach().contiguous())
-            try:
-                x._ipr_col = (col, x._version)     # an in-place edit of the image bumps _version and voids it
-            except Exception:
-                pass
+            if getattr(module, "_ipr_keep_col", False):
+                try:
+                    x._ipr_col = (col, x._version)     # an in-place edit of the image bumps _version and voids it
+                except Exception:
+                    pass
         a, _ = P.first.run(col, P.packs.get("c0"), epi=dense.EPI_BIAS_LRELU, slope=0.1, sigma=sig[0], bias=bs[0].detach())
         acts = [a]
         for i, plan in enumerate(P.conv):

@@ -26,7 +26,11 @@ class Arena(object):
         self.param = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.version = 0                                          # bumped by whoever rewrites the masters
-        self.clean = True                                         # gradient arena known to be all zeros
+        # ``clean``: gradient arena known to be all zeros.  Only honoured when ``track_clean`` is set by an owner that
+        # controls every writer (the native DCGAN step: all gradients arrive through engine.py, which flags the arena
+        # dirty, and FlatAdam clears it as it consumes it); otherwise zero_grad() always clears.
+        self.clean = True
+        self.track_clean = False
         self.slots = None                                         # 4 floats riding behind/before the gradients
         self.reduce_view = self.grad                              # what a data-parallel all-reduce covers
         with torch.no_grad():
@@ -52,7 +56,7 @@ class Arena(object):
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
 
     def zero_grad(self):
-        if not self.clean:                  # FlatAdam clears the arena as it consumes it: usually nothing to do
+        if not (self.track_clean and self.clean):   # FlatAdam clears the arena as it consumes it: usually nothing to do
             self.grad.zero_()
             self.clean = True
         self.bind_grads()

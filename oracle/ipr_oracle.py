@@ -352,7 +352,8 @@ class DCGANStepOracle:
         self.blackbox, self.whitebox = blackbox, whitebox
         self.layers = norm_layers(G)
         if whitebox:
-            self.signs = signature_signs(string, [m.weight.numel() for _, m in self.layers])
+            dev = next(G.parameters()).device        # CPU in the parity tests; bench.py's eager-GPU arm moves it
+            self.signs = [s.to(dev) for s in signature_signs(string, [m.weight.numel() for _, m in self.layers])]
             with torch.no_grad():  # tools/sign_model.py:39
                 for (_, m), s in zip(self.layers, self.signs):
                     m.weight.abs_().mul_(s)

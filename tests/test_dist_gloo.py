@@ -33,7 +33,8 @@ def _worker(rank, world, port, out):
         arena.zero_grad()
         torch.nn.functional.mse_loss(net(xs), ys).backward()    # accumulates into the arena views
         assert float(arena.grad.abs().sum()) > 0
-        ipr_dist.allreduce_mean_(arena.grad)
+        ipr_dist.allreduce_sum_(arena.reduce_view)               # what FlatAdam.step() issues; 1/world rides in Adam
+        arena.grad.mul_(1.0 / world)
         # reference: the full batch on one process
         torch.manual_seed(0)
         ref = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 3))
@@ -73,3 +74,27 @@ def test_arena_views_and_zero_grad():
     assert float(arena.grad.abs().sum()) == 0 and all(p.grad is not None for p in net.parameters())
     sd = net.state_dict()
     assert list(sd.keys()) == ["0.weight", "0.bias", "1.weight", "1.bias"]
+
+
+def test_shared_gradient_buffer_layout():
+    """[D grads | D slots | G slots | G grads]: each network's all-reduce range covers its gradients and its own four
+    metric slots and nothing of the other network; the eight slots are one contiguous board."""
+    from ipr_gan_b200 import flat
+    d = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 1))
+    g = torch.nn.Sequential(torch.nn.Linear(3, 6), torch.nn.Linear(6, 5))
+    ad, ag = flat.arena_for(list(d.parameters())), flat.arena_for(list(g.parameters()))
+    d(torch.randn(2, 5)).sum().backward()
+    before = [p.grad.clone() for p in d.parameters()]
+    board = flat.share_gradient_buffer(ad, ag)
+    assert board.numel() == 8 and board.data_ptr() == ad.grad.data_ptr() + 4 * ad.numel
+    assert ag.grad.data_ptr() == board.data_ptr() + 32 and ag.grad.data_ptr() % 16 == 0
+    assert ad.reduce_view.data_ptr() == ad.grad.data_ptr() and ad.reduce_view.numel() == ad.numel + 4
+    assert ag.reduce_view.data_ptr() == ag.slots.data_ptr() and ag.reduce_view.numel() == ag.numel + 4
+    assert ad.slots.data_ptr() == board.data_ptr() and ag.slots.data_ptr() == board.data_ptr() + 16
+    for p, b in zip(d.parameters(), before):                       # gradients survived the move, views re-bound
+        assert torch.equal(p.grad, b) and ad.grad.data_ptr() <= p.grad.data_ptr() < board.data_ptr()
+    board.fill_(3.0)
+    ad.zero_grad(), ag.zero_grad()
+    assert float(board.sum()) == 24.0 and float(ad.grad.abs().sum()) == 0     # zero_grad leaves the board alone
+    g(torch.randn(2, 3)).sum().backward()
+    assert float(ag.grad.abs().sum()) > 0 and float(board.sum()) == 24.0

@@ -304,12 +304,15 @@ def test_packed_weights_follow_the_masters():
     G.load_state_dict(other)
     Go.load_state_dict(other)
     assert rel(G(z.cuda()), Go(z)) < 2e-2
-    opt, opto = torch.optim.SGD(G.parameters(), lr=0.5), torch.optim.SGD(Go.parameters(), lr=0.5)
+    opt, opto = torch.optim.SGD(G.parameters(), lr=0.02), torch.optim.SGD(Go.parameters(), lr=0.02)
     gsel = torch.randn(8, 3, 32, 32)
-    G(z.cuda()).backward(gsel.cuda())
+    stale = G(z.cuda())
+    stale.backward(gsel.cuda())
     Go(z).backward(gsel)
     opt.step(), opto.step()
-    assert rel(G(z.cuda()), Go(z)) < 4e-2                              # one SGD step on bf16 vs fp32 gradients
+    fresh, want = G(z.cuda()), Go(z)
+    assert rel(fresh, want) < 4e-2                                     # one SGD step on bf16 vs fp32 gradients
+    assert rel(stale, want) > 2 * rel(fresh, want)                     # ... and the step really moved the output
     with torch.no_grad():
         G.convs[3].weight[:, 0] = 0.0
         Go.convs[3].weight[:, 0] = 0.0
