@@ -304,15 +304,17 @@ def test_packed_weights_follow_the_masters():
     G.load_state_dict(other)
     Go.load_state_dict(other)
     assert rel(G(z.cuda()), Go(z)) < 2e-2
-    opt, opto = torch.optim.SGD(G.parameters(), lr=0.02), torch.optim.SGD(Go.parameters(), lr=0.02)
-    gsel = torch.randn(8, 3, 32, 32)
-    stale = G(z.cuda())
-    stale.backward(gsel.cuda())
-    Go(z).backward(gsel)
+    # a stock torch optimizer: the SAME (prescribed) gradients on both sides, so only the weight hand-over is tested
+    opt, opto = torch.optim.SGD(G.parameters(), lr=1.0), torch.optim.SGD(Go.parameters(), lr=1.0)
+    stale = G(z.cuda()).detach()
+    for p_, q_ in zip(G.parameters(), Go.parameters()):
+        g_ = 0.02 * torch.randn_like(q_)
+        q_.grad = g_
+        p_.grad.copy_(g_) if p_.grad is not None else setattr(p_, "grad", g_.cuda())
     opt.step(), opto.step()
     fresh, want = G(z.cuda()), Go(z)
-    assert rel(fresh, want) < 4e-2                                     # one SGD step on bf16 vs fp32 gradients
-    assert rel(stale, want) > 2 * rel(fresh, want)                     # ... and the step really moved the output
+    assert rel(fresh, want) < 2e-2
+    assert rel(stale, want) > 5 * rel(fresh, want)                     # ... and the step really moved the output
     with torch.no_grad():
         G.convs[3].weight[:, 0] = 0.0
         Go.convs[3].weight[:, 0] = 0.0
