@@ -372,6 +372,58 @@ int ipr_gen_adv_loss_f32(const float *logits, int batch, float loss_scale, float
  * replacing the host-side torch.randn + H2D copy of experiments/image_generation.py:94. */
 int ipr_randn_f32(float *out, int64_t n, uint64_t seed, uint64_t *counter, uint32_t *ticket, ipr_stream_t stream);
 
+/* ------------------------------------------------------------------ generic layers (csrc/layers.cu)
+ * The SRGAN / CycleGAN network families (networks/sr_resnet.py:3-44, discriminator_96.py:3-35,
+ * resnet_generator.py:3-59, conv_discriminator.py:3-21): a convolution of any of their shapes is
+ *   ipr_im2col_nhwc_bf16 (patch matrix)  ->  ipr_tapgemm_bf16 (single-tap "linear" GEMM on tcgen05),
+ * its data gradient  ipr_tapgemm_bf16 (dY x W^T)  ->  ipr_col2im_nhwc_bf16 (adjoint gather),
+ * its weight gradient  ipr_wgrad_bf16 (dY^T x patch matrix).
+ *
+ * Patch matrix of an NHWC bf16 tensor x (n,h,w,c; c % 8 == 0):
+ *   col[(img, oy, ox)][(ky*k + kx)*c + ch] = x[img, src(oy*stride + ky - pad), src(ox*stride + kx - pad), ch]
+ * rows are kp elements long (kp % 8 == 0, kp >= k*k*c, the tail is zero).  src(): zero outside the image, or
+ * (reflect != 0) mirrored without repeating the edge (nn.ReflectionPad2d); up > 1 runs a transposed convolution
+ * as a direct one over the zero-inserted grid (coordinates not divisible by up, or past (size-1)*up, read zero). */
+int ipr_im2col_nhwc_bf16(const void *x, void *col, int n, int h, int w, int c, int oh, int ow, int k, int stride,
+                         int pad, int up, int reflect, int kp, ipr_stream_t stream);
+/* Adjoint of the above: dx[img, iy, ix, ch] = addend (optional, same shape) + sum of every dcol entry that read it. */
+int ipr_col2im_nhwc_bf16(const void *dcol, void *dx, const void *addend, int n, int h, int w, int c, int oh, int ow,
+                         int k, int stride, int pad, int up, int reflect, int kp, ipr_stream_t stream);
+/* Module boundary: NCHW fp32 -> NHWC bf16 with channels zero-padded to cp (cp % 8 == 0); tanh_out (optional, same
+ * shape as x) multiplies by 1 - tanh_out^2 (backward of a final Tanh fused into the gradient's layout change). */
+int ipr_nchw_to_nhwc_bf16(const float *x, const float *tanh_out, void *y, int64_t n, int c, int h, int w, int cp,
+                          ipr_stream_t stream);
+/* fp32 GEMM result t[pixel][ld] (+ bias[ch], optional) -> NCHW fp32 (first c columns), optional Tanh. */
+int ipr_finish_nchw_f32(const float *t, const float *bias, float *out, int64_t n, int c, int h, int w, int ld,
+                        int tanh_out, ipr_stream_t stream);
+/* nn.PixelShuffle(2) on NHWC bf16: y[n,2h+i,2w+j,c] = x[n,h,w,c*4+i*2+j] (inverse != 0: x is the large grid). */
+int ipr_pixel_shuffle2_nhwc_bf16(const void *x, void *y, int64_t n, int h, int w, int c_out, int inverse,
+                                 ipr_stream_t stream);
+int ipr_add_bf16(const void *a, const void *b, void *out, int64_t n, ipr_stream_t stream);
+
+/* Normalisation (+ activation, + residual) over an NHWC bf16 tensor viewed as [groups][rows][channels]:
+ * groups = 1 is BatchNorm2d in training mode (statistics over all rows; running statistics and
+ * num_batches_tracked updated when given), groups = batch is InstanceNorm2d (per image).
+ * has_norm: 0 = activation only, 1 = normalise with the statistics of x, 2 = normalise with the given
+ * scale / shift (eval-mode BatchNorm).  scale/shift/mean/rstd: [groups][channels] outputs kept for the backward.
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 PReLU (single parameter, read from slope_ptr), 4 Tanh.
+ * y = act(x * scale + shift) + residual (optional).  gamma / beta NULL = non-affine. */
+size_t ipr_norm_workspace_bytes(int groups, int channels);
+int ipr_norm_fwd_bf16(const void *x, void *y, const void *residual, int groups, int64_t rows, int channels,
+                      int has_norm, float eps, float momentum, const float *gamma, const float *beta,
+                      float *running_mean, float *running_var, int64_t *num_batches_tracked, float *scale,
+                      float *shift, float *mean, float *rstd, int act, float slope, const float *slope_ptr,
+                      void *workspace, size_t workspace_bytes, ipr_stream_t stream);
+/* Backward of the above (x = the forward's raw input): dx; dgamma / dbeta (+)= (optional); *dslope (+)= PReLU slope
+ * gradient (optional).  sign != NULL adds the white-box sign-loss gradient
+ * -sign_scale * sign_c / channels * [gamma0 - gamma_c*sign_c > 0] to dgamma (tools/sign_model.py:42-49), for
+ * BatchNorm and InstanceNorm alike. */
+int ipr_norm_bwd_bf16(const void *dy, const void *x, void *dx, int groups, int64_t rows, int channels, int has_norm,
+                      const float *gamma, const float *scale, const float *shift, const float *mean,
+                      const float *rstd, float *dgamma, float *dbeta, int accumulate, const float *sign, float gamma0,
+                      float sign_scale, int act, float slope, const float *slope_ptr, float *dslope, void *workspace,
+                      size_t workspace_bytes, ipr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,17 @@ SIGNATURES = {
     "ipr_gather_pack_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ipr_hinge_d_loss_f32": (c_int, [c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ipr_gen_adv_loss_f32": (c_int, [c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr]),
+    "ipr_im2col_nhwc_bf16": (c_int, [c_ptr, c_ptr] + [c_int] * 12 + [c_ptr]),
+    "ipr_col2im_nhwc_bf16": (c_int, [c_ptr, c_ptr, c_ptr] + [c_int] * 12 + [c_ptr]),
+    "ipr_nchw_to_nhwc_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_ptr]),
+    "ipr_finish_nchw_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_ptr]),
+    "ipr_pixel_shuffle2_nhwc_bf16": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_ptr]),
+    "ipr_add_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ipr_norm_workspace_bytes": (c_size, [c_int, c_int]),
+    "ipr_norm_fwd_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_int, c_int, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr,
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_size, c_ptr]),
+    "ipr_norm_bwd_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                  c_ptr, c_int, c_ptr, c_f32, c_f32, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "ipr_randn_f32": (c_int, [c_ptr, c_i64, ctypes.c_uint64, c_ptr, c_ptr, c_ptr]),
     "ipr_wgrad_tiles": (c_int, [c_ptr]),
     "ipr_wgrad_reduce_f32": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_int, c_f32, c_ptr]),

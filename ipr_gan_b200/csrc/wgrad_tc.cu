@@ -192,6 +192,7 @@ wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int phases, int n_
     }
     for (; s < splits; s++) acc += src[(size_t)s * split_stride];
     const int rn = row_map ? __ldg(row_map + n) : n;
+    if (rn < 0) return;                                  // padding row of the GEMM (N padded to a multiple of 16)
     float *dst = grad + (size_t)rn * s_n + off;
     *dst = accumulate ? *dst + acc * scale : acc * scale;
 }

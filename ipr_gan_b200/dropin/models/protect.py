@@ -183,16 +183,22 @@ class WhiteBoxWrapper(Wrapper):
         self.loss_model = tools.SignLossModel(target, self.config).to(self.device[0])
         self._modules["sign"] = self.loss_model
         self._sign_hook = None
+        self._sign_slot = None
         import networks
-        if self.board is not None and isinstance(target.module, networks.ConvGenerator):
+        fused_dcgan = self.board is not None and isinstance(target.module, networks.ConvGenerator)
+        if fused_dcgan or getattr(target.module, "_ipr_native_norms", False):
+            # the target's normalisation layers run on this library: d(sign loss)/d(gamma) is added inside their
+            # backward launches (BatchNorm and InstanceNorm alike), the value is one launch over all gammas
             _, signs = self.loss_model._collect(target)
             self._sign_hook = _SignHook(self.loss_model, signs)
             object.__setattr__(target.module, "_ipr_sign_hook", self._sign_hook)
+            if not fused_dcgan:
+                self._sign_slot = torch.zeros(1, device=self.device[0])
 
     def compute_g_loss(self):
         target = getattr(self.model, self.config.target)
         self.LossG = self.model.LossG
-        board = self.board if self._sign_hook is not None else None
+        board = self.board if (self._sign_hook is not None and self._sign_slot is None) else None
         if board is not None:
             if self.inhibit:
                 board.slot(board.P_SIGN).zero_()
@@ -201,6 +207,13 @@ class WhiteBoxWrapper(Wrapper):
                 self.loss_model.value_into(target, board.slot(board.P_SIGN), board.loss_scale)
                 self._sign_hook.arm()
             self.LossS = board.scalar(board.P_SIGN)
+        elif self._sign_hook is not None:
+            if self.inhibit:
+                self.LossS = torch.zeros_like(self.LossG)
+            else:
+                self.loss_model.value_into(target, self._sign_slot, 1.0)
+                self._sign_hook.arm()
+                self.LossS = self._sign_slot[0]      # a constant in the autograd graph: its gradient rides in the hook
         else:
             self.LossS = torch.zeros_like(self.LossG) if self.inhibit else self.loss_model(target)
         if hasattr(self.model, "LossW"):
@@ -216,7 +229,7 @@ class WhiteBoxWrapper(Wrapper):
     def get_metrics(self):
         metrics = self.model.get_metrics()
         if not self.inhibit:
-            board = self.board if self._sign_hook is not None else None
+            board = self.board if (self._sign_hook is not None and self._sign_slot is None) else None
             s = board.fetch()[board.P_SIGN] if board is not None else self.LossS.item()
             metrics["P/SignLoss"] = s
             metrics["G/Sum"] += s

@@ -8,7 +8,7 @@ reference checkout (``ipr_gan_b200.refpath``) -- they stay plain PyTorch and not
 from ipr_gan_b200 import refpath as _refpath
 from networks.dcgan_nets import (ConvGenerator, ConvGenerator32, ConvGenerator64, SNDiscriminator,  # noqa: F401
                                  SNDiscriminator32, SNDiscriminator64)
-from networks.torch_nets import (ConvDiscriminator, Discriminator96, Resnet6Blocks, Resnet9Blocks,  # noqa: F401
+from networks.seq_nets import (ConvDiscriminator, Discriminator96, Resnet6Blocks, Resnet9Blocks,  # noqa: F401
                                  ResnetGenerator, SRResNet, VGG19Feature)
 
 __getattr__ = _refpath.passthrough("networks", {

@@ -4,13 +4,24 @@
   Resnet{6,9}Blocks  networks/resnet_generator.py:3-59   ConvDiscriminator   networks/conv_discriminator.py:3-21
   VGG19Feature       networks/vgg.py:5-40 (frozen extractor; out of the accelerated scope)
 
-STATUS (round 1): these convolutions (k9 / k7 / k6 / k1 kernels, PixelShuffle, reflection padding, InstanceNorm,
-24- and 96-pixel-wide grids) are not on the tcgen05 tap GEMM yet, so the dense layers of these two model families
-run as PyTorch ops.  Everything IPR-specific around them -- noise-patch trigger, watermark paste / crop, SSIM
-watermark loss forward+backward, sign loss and BER over the BatchNorm / InstanceNorm gammas, pHash verification --
-runs on the library's sm_100a kernels through the same wrappers as DCGAN (SURVEY.md 8f rank 3 is the next step).
+As with the DCGAN networks the child modules are ONLY the parameter / state containers: ``forward`` hands the module
+tree to ``ipr_gan_b200.seqnet``, which lowers it to conv / norm / activation blocks and runs the whole network as one
+autograd node over the library's kernels -- every convolution (k 1..9, stride 1/2, reflection or zero border,
+transposed) on the tcgen05 GEMM through a patch matrix, BatchNorm / InstanceNorm / PReLU / PixelShuffle in
+csrc/layers.cu, NHWC bf16 inside, NCHW fp32 at the module boundary.  No CPU or PyTorch-op path: a non-CUDA input
+raises (``torch.nn.Sequential.forward(net, x)`` still evaluates the same tree with PyTorch operators; the parity
+tests use exactly that as the fp32 reference).
 """
 import torch.nn as nn
+
+
+def _native(net, x, who):
+    if not x.is_cuda:
+        from ipr_gan_b200.ops import IprError
+        raise IprError("%s.forward computes on CUDA only (libipr_b200.so, sm_100a); got a %s tensor -- move the "
+                       "module and its input to a CUDA device" % (who, x.device.type))
+    from ipr_gan_b200 import seqnet
+    return seqnet.forward(net, x)
 
 
 # ------------------------------------------------------------------------------------------------ SRResNet
@@ -41,12 +52,17 @@ class _Up2(nn.Sequential):
 
 
 class SRResNet(nn.Sequential):
+    _ipr_native_norms = True            # BatchNorm backward runs in csrc/layers.cu (sign-loss gradient fused there)
+
     def __init__(self, n_block=16):
         trunk = [_Skip(nn.Sequential(_SRConv(64, 64, 3, 1, 1, n=True, a=nn.PReLU()), _SRConv(64, 64, 3, 1, 1, n=True)))
                  for _ in range(n_block)]
         trunk.append(_SRConv(64, 64, 3, 1, 1, n=True))
         super().__init__(_SRConv(3, 64, 9, 1, 4, a=nn.PReLU()), _Skip(nn.Sequential(*trunk)),
                          _Up2(64, 64), _Up2(64, 64), _SRConv(64, 3, 9, 1, 4))
+
+    def forward(self, x):
+        return _native(self, x, "SRResNet")
 
 
 # ------------------------------------------------------------------------------------------------ Discriminator96
@@ -65,7 +81,7 @@ class Discriminator96(nn.Sequential):
                          nn.Conv2d(512, 1024, 6, 1, 0), nn.LeakyReLU(0.2, True), nn.Conv2d(1024, 1, 1, 1, 0))
 
     def forward(self, x):
-        return super().forward(x).squeeze()
+        return _native(self, x, "Discriminator96").squeeze()
 
 
 # ------------------------------------------------------------------------------------------------ CycleGAN
@@ -82,6 +98,8 @@ class ResnetBlock(nn.Module):
 
 
 class ResnetGenerator(nn.Sequential):
+    _ipr_native_norms = True            # InstanceNorm backward runs in csrc/layers.cu (sign-loss gradient fused there)
+
     def __init__(self, n_block):
         seq = [nn.ReflectionPad2d(3), nn.Conv2d(3, 64, 7, 1, 0), nn.InstanceNorm2d(64, affine=True), nn.ReLU(True)]
         for ch in (64, 128):
@@ -92,6 +110,9 @@ class ResnetGenerator(nn.Sequential):
                     nn.ReLU(True)]
         seq += [nn.ReflectionPad2d(3), nn.Conv2d(64, 3, 7, 1, 0), nn.Tanh()]
         super().__init__(*seq)
+
+    def forward(self, x):
+        return _native(self, x, "ResnetGenerator")
 
 
 def Resnet9Blocks():
@@ -109,6 +130,9 @@ class ConvDiscriminator(nn.Sequential):
                          nn.Conv2d(128, 256, 4, 2, 1), nn.InstanceNorm2d(256), nn.LeakyReLU(0.2, True),
                          nn.Conv2d(256, 512, 4, 1, 1), nn.InstanceNorm2d(512), nn.LeakyReLU(0.2, True),
                          nn.Conv2d(512, 1, 4, 1, 1))
+
+    def forward(self, x):
+        return _native(self, x, "ConvDiscriminator")
 
 
 # ------------------------------------------------------------------------------------------------ VGG feature net

@@ -1,0 +1,158 @@
+"""GPU: the SRGAN / CycleGAN network families on the native engine (ipr_gan_b200/seqnet.py: patch matrix + tcgen05
+GEMM convolutions, csrc/layers.cu normalisation / activation kernels) against PyTorch (oracle/seq_oracle.py).
+
+Tolerances: bf16 tensor-core convolutions, north_star budget 2e-2.
+* every layer shape on its own, identical inputs: forward, data gradient, weight / bias / gamma / beta / PReLU
+  gradients within 1e-2 of the tensor scale of the fp32 PyTorch op on the same bf16-rounded operands;
+* whole networks at the BASELINE shapes (config 3: 16 x 3 x 24 x 24 -> 96 x 96; config 4: 1 x 3 x 128 x 128):
+  outputs and every parameter gradient within 2e-2 (relative Frobenius norm) of the oracle evaluated with the
+  engine's bf16 storage points (so both sides see the same ReLU / LeakyReLU / PReLU patterns), and outputs within
+  3e-2 of the pure fp32 evaluation (24-37 blocks of bf16 storage in a row)."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+class _Net(nn.Sequential):
+    """A small stack run natively: the block under test followed by a plain 1x1 convolution (the engine's last block
+    is always a bare convolution)."""
+
+    def forward(self, x):
+        from ipr_gan_b200 import seqnet
+        return seqnet.forward(self, x)
+
+
+class _Skip(nn.Module):
+    def __init__(self, block):
+        super().__init__()
+        self.block = block
+
+    def forward(self, x):
+        return x + self.block(x)
+
+
+LAYERS = {
+    "conv3+bn+prelu": lambda: [nn.Conv2d(64, 64, 3, 1, 1), nn.BatchNorm2d(64), nn.PReLU()],
+    "conv9(3ch)+prelu": lambda: [nn.Conv2d(3, 64, 9, 1, 4), nn.PReLU()],
+    "conv3+shuffle+prelu": lambda: [nn.Conv2d(64, 256, 3, 1, 1), nn.PixelShuffle(2), nn.PReLU()],
+    "conv3s2+bn+lrelu": lambda: [nn.Conv2d(64, 128, 3, 2, 1), nn.BatchNorm2d(128), nn.LeakyReLU(0.2, True)],
+    "conv3(3ch)+lrelu": lambda: [nn.Conv2d(3, 64, 3, 1, 1), nn.LeakyReLU(0.2, True)],
+    "conv6valid+lrelu": lambda: [nn.Conv2d(64, 128, 6, 1, 0), nn.LeakyReLU(0.2, True)],
+    "reflect3+conv7(3ch)+in+relu": lambda: [nn.ReflectionPad2d(3), nn.Conv2d(3, 64, 7, 1, 0), nn.InstanceNorm2d(64, affine=True),
+                                            nn.ReLU(True)],
+    "resblock(reflect,in)": lambda: [nn.Conv2d(3, 64, 3, 1, 1), nn.ReLU(True),
+                                     _Skip(nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(64, 64, 3, 1, 0),
+                                                         nn.InstanceNorm2d(64, affine=True), nn.ReLU(True),
+                                                         nn.ReflectionPad2d(1), nn.Conv2d(64, 64, 3, 1, 0),
+                                                         nn.InstanceNorm2d(64, affine=True)))],
+    "convT3s2op1+in+relu": lambda: [nn.Conv2d(3, 128, 3, 1, 1), nn.ReLU(True),
+                                    nn.ConvTranspose2d(128, 64, 3, 2, 1, output_padding=1), nn.InstanceNorm2d(64, affine=True),
+                                    nn.ReLU(True)],
+    "conv4s2+in(no affine)+lrelu": lambda: [nn.Conv2d(3, 64, 4, 2, 1), nn.LeakyReLU(0.2, True), nn.Conv2d(64, 128, 4, 2, 1),
+                                            nn.InstanceNorm2d(128), nn.LeakyReLU(0.2, True)],
+    "conv4s1": lambda: [nn.Conv2d(3, 64, 4, 1, 1), nn.LeakyReLU(0.2, True)],
+}
+
+
+def _randomise(net):
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.InstanceNorm2d)) and m.weight is not None:
+                m.weight.copy_(torch.randn_like(m.weight) * 0.3 + 1.0)
+                m.bias.copy_(torch.randn_like(m.bias) * 0.1)
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) and m.bias is not None:
+                m.bias.copy_(torch.randn_like(m.bias) * 0.05)
+
+
+def _check_against_sim(net, x, fwd_tol, grad_tol, need_dx=True):
+    from ipr_gan_b200 import seqnet
+    from oracle import seq_oracle as so
+    ref_net = copy.deepcopy(net).cpu()
+    net = net.cuda()
+    xg = x.clone().cuda().requires_grad_(need_dx)
+    xs = x.clone().requires_grad_(need_dx)
+    out = net(xg)
+    sim = so.forward_sim_bf16(ref_net, xs, seqnet.lower(ref_net))
+    assert out.shape == sim.shape, (out.shape, sim.shape)
+    assert rel(out, sim) < fwd_tol, ("forward", rel(out, sim))
+    g = torch.randn_like(sim)
+    out.backward(g.cuda())
+    sim.backward(g)
+    worst = {}
+    if need_dx:
+        worst["x"] = rel(xg.grad, xs.grad)
+    for (n, p), (_, q) in zip(net.named_parameters(), ref_net.named_parameters()):
+        assert p.grad is not None, n
+        worst[n] = rel(p.grad, q.grad)
+    bad = {k: v for k, v in worst.items() if not v < grad_tol}
+    assert not bad, bad
+    for (n, b), (_, c) in zip(net.named_buffers(), ref_net.named_buffers()):       # BatchNorm running statistics
+        assert rel(b.float(), c.float()) < 1e-2, n
+    return out, sim
+
+
+@pytest.mark.parametrize("name", sorted(LAYERS))
+def test_layer_shapes(name):
+    torch.manual_seed(1)
+    layers = LAYERS[name]()
+    width = [m for m in layers if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d))][-1]
+    skip = [m for m in layers if isinstance(m, _Skip)]
+    last_c = 64 if skip else (width.out_channels // (4 if any(isinstance(m, nn.PixelShuffle) for m in layers) else 1))
+    net = _Net(*layers, nn.Conv2d(last_c, 3, 1, 1, 0))
+    _randomise(net)
+    first = [m for m in net.modules() if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d))][0]
+    x = torch.rand(3, first.in_channels, 20, 22) * 2 - 1
+    _check_against_sim(net, x, fwd_tol=1e-2, grad_tol=2e-2)
+
+
+NETS = [("SRResNet", (16, 3, 24, 24)), ("Discriminator96", (16, 3, 96, 96)), ("Resnet9Blocks", (1, 3, 128, 128)),
+        ("ConvDiscriminator", (1, 3, 128, 128)), ("Resnet9Blocks", (2, 3, 64, 64)), ("SRResNet", (3, 3, 24, 24))]
+
+
+@pytest.mark.parametrize("name,shape", NETS, ids=["%s-%s" % (n, "x".join(map(str, s))) for n, s in NETS])
+def test_networks_at_baseline_shapes(name, shape):
+    import networks
+    from oracle import seq_oracle as so
+    torch.manual_seed(2)
+    net = getattr(networks, name)()
+    _randomise(net)
+    x = torch.rand(*shape) * 2 - 1
+    pure = so.forward_fp32(copy.deepcopy(net), x)
+    out, sim = _check_against_sim(net, x, fwd_tol=1e-2, grad_tol=2e-2)
+    assert rel(out, pure) < 3e-2, rel(out, pure)
+    sd = net.state_dict()
+    assert all(torch.isfinite(v.float()).all() for v in sd.values())
+
+
+def test_eval_mode_and_no_cpu_fallback():
+    import networks
+    from ipr_gan_b200 import ops
+    from oracle import seq_oracle as so
+    torch.manual_seed(3)
+    net = networks.SRResNet()
+    with pytest.raises(ops.IprError):
+        net(torch.rand(1, 3, 24, 24))
+    x = torch.rand(4, 3, 24, 24)
+    net = net.cuda().train()
+    net(x.cuda())                                   # moves the running statistics
+    net.eval()
+    ref = copy.deepcopy(net).cpu()
+    with torch.no_grad():
+        assert rel(net(x.cuda()), so.forward_fp32(ref, x)) < 3e-2
+    # trigger pass semantics (models/util.py:55-69): batch statistics, running statistics untouched
+    from models.util import DisableBatchNormStats
+    net.train()
+    before = {k: v.clone() for k, v in net.state_dict().items() if "running" in k or "tracked" in k}
+    with DisableBatchNormStats(net):
+        net(x.cuda() * 0.5)
+    after = net.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before)

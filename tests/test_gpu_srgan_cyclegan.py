@@ -1,8 +1,9 @@
 """GPU: protected IPR-SRGAN (config 3 shape: 24 -> 96) and IPR-CycleGAN (config 4: Resnet9Blocks, InstanceNorm sign
 loss) steps through the drop-in models / wrappers against metrics recorded from the UNMODIFIED reference
-(tests/golden/srgan_cyclegan_steps.npz, oracle/make_golden.py).  The dense layers of these two families still run as
-fp32 PyTorch ops (see networks/torch_nets.py); triggers, SSIM watermark loss and sign loss run on the sm_100a kernels.
-Tolerance 5e-3: fp32 cuDNN vs fp32 MKL-DNN convolution algorithms through 30-50 layers."""
+(tests/golden/srgan_cyclegan_steps.npz, oracle/make_golden.py).  Generators and discriminators run natively
+(ipr_gan_b200/seqnet.py: tcgen05 convolutions with bf16 operands); triggers, SSIM watermark loss and sign loss run on the
+sm_100a kernels; the frozen VGG feature extractor is outside the accelerated path (PyTorch).
+Tolerance 2e-2 (north_star, bf16 convolutions) on every metric."""
 import os
 
 import numpy as np
@@ -18,7 +19,7 @@ def _cfg(d):
     return Config(d)
 
 
-def _close(got, keys, want, tol=5e-3):
+def _close(got, keys, want, tol=2e-2):
     assert sorted(got) == [str(k) for k in keys]
     for k, w in zip(keys, want):
         g = got[str(k)]
@@ -48,7 +49,7 @@ def test_srgan_protected_steps(golden, watermark_path):
     sr.update_g({"low_res": lr, "high_res": hr, "pretrain": False})
     sr.update_d({"high_res": sr.high_res, "super_res": sr.super_res})
     _close(sr.get_metrics(), g["sr_gan_keys"], g["sr_gan"])
-    assert np.allclose(sr.super_res[:1, :, :8, :8].detach().cpu().numpy(), g["sr_super_res"], atol=5e-3)
+    assert np.allclose(sr.super_res[:1, :, :8, :8].detach().cpu().numpy(), g["sr_super_res"], atol=2e-2)
     assert list(sr.state_dict().keys()) == [str(k) for k in g["sr_state_keys"]]
     assert list(sr.state_dict()["sign"].keys())[:3] == [str(k) for k in g["sr_sign_keys"]]
     assert sr.loss_model.compute_ber_counts(sr.G) == (0, 33 * 64)          # 2 112 signature bits in 33 BatchNorm layers
@@ -77,6 +78,6 @@ def test_cyclegan_protected_step(golden, watermark_path):
     cg.update_g({"real_A": a, "real_B": b})
     cg.update_d({"real_A": cg.real_A, "real_B": cg.real_B, "fake_A": cg.fake_A.detach(), "fake_B": cg.fake_B.detach()})
     _close(cg.get_metrics(), g["cg_keys"], g["cg"])
-    assert np.allclose(cg.fake_A[:1, :, :8, :8].detach().cpu().numpy(), g["cg_fake_A"], atol=5e-3)
+    assert np.allclose(cg.fake_A[:1, :, :8, :8].detach().cpu().numpy(), g["cg_fake_A"], atol=2e-2)
     assert list(cg.state_dict().keys()) == [str(k) for k in g["cg_state_keys"]]
     assert cg.loss_model.compute_ber_counts(cg.GB) == (0, 5248)            # 23 InstanceNorm layers of Resnet9Blocks
