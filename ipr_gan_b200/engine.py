@@ -279,6 +279,9 @@ def _tap27_rows_layout(w):
 
 
 class GenPlans(object):
+    def __deepcopy__(self, memo):       # plans hold device buffers and events: a copied module builds its own
+        return None
+
     def __init__(self, module):
         mg = module.mg
         self.mg = mg
@@ -321,6 +324,9 @@ class GenPlans(object):
 
 
 class DisPlans(object):
+    def __deepcopy__(self, memo):
+        return None
+
     def __init__(self, module):
         md = module.md
         self.md = md

@@ -25,6 +25,8 @@ from ._lib import check, lib
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_PRELU, ACT_TANH = 0, 1, 2, 3, 4
 
+CAPTURE = None         # test hook: a list that receives every block's (raw conv output, activation output), NHWC bf16
+
 
 def _up(v, m):
     return (v + m - 1) // m * m
@@ -59,7 +61,8 @@ class Block(object):
             self.stride, self.up, self.pad, self.reflect = s, 1, (reflect or p), int(bool(reflect))
             self.cin, self.cout = conv.in_channels, conv.out_channels
         self.cin_p, self.n_p = _up(self.cin, 8), _up(self.cout, 16)
-        self.kp = _up(k * k * self.cin_p, 16)
+        # 32: the weight-gradient GEMM's epilogue stores 32-column chunks (a narrower row would spill into the next one)
+        self.kp = _up(k * k * self.cin_p, 32)
         self.norm = None
         self.shuffle = False
         self.act, self.slope, self.prelu = ACT_NONE, 0.0, None
@@ -165,6 +168,9 @@ def lower(net):
 
 # ----------------------------------------------------------------------------------------- plans
 class NetPlans(object):
+    def __deepcopy__(self, memo):       # plans hold device buffers and events: a copied module builds its own
+        return None
+
     def __init__(self, net):
         self.blocks = lower(net)
         self.params = list(net.parameters())
@@ -304,6 +310,8 @@ class _SeqFn(torch.autograd.Function):
                                           _p(gamma), _p(beta), _p(rm), _p(rv), _p(nbt), _p(scale), _p(shift), _p(mean),
                                           _p(rstd), b.act, float(b.slope), _p(slope_ptr), _p(ws), nbytes, _st()),
                   "ipr_norm_fwd_bf16")
+            if CAPTURE is not None:
+                CAPTURE.append((y0, z))               # z before PixelShuffle: its sign pattern is the activation mask
             if b.shuffle:
                 z = _shuffle(z, False)
             rec.update(y0=y0, groups=groups, rows=rows, has_norm=has_norm, scale=scale, shift=shift, mean=mean, rstd=rstd)

@@ -45,8 +45,18 @@ def forward_fp32(net, x):
     return y.squeeze() if type(net).__name__ == "Discriminator96" else y
 
 
-def forward_sim_bf16(net, x, blocks):
-    """``blocks`` = ipr_gan_b200.seqnet.lower(net).  x: NCHW fp32."""
+def _gate(y, mask, slope):
+    """Activation with a PRESCRIBED on/off pattern: y where mask else slope * y, forward and backward."""
+    return y * torch.where(mask, torch.ones((), dtype=y.dtype), slope * torch.ones((), dtype=y.dtype))
+
+
+def forward_sim_bf16(net, x, blocks, capture=None, masks=None):
+    """``blocks`` = ipr_gan_b200.seqnet.lower(net).  x: NCHW fp32.  ``capture``: optional list receiving every block's
+    (rounded convolution output, block output) in NCHW.  ``masks``: optional per-block boolean NCHW tensors (None for
+    blocks without a piecewise-linear activation) prescribing the ReLU / LeakyReLU / PReLU on/off pattern -- the
+    engine's own.  Two bf16 evaluations of a deep network differ by about one bf16 ulp per layer (each side rounds a
+    slightly different fp32 value), which moves ~1 % of the pre-activations across zero; every such element changes
+    its gradient by 100 %.  With the pattern prescribed, what remains is arithmetic."""
     r, wq = _RoundBoth.apply, _RoundFwd.apply
     tensors = [_RoundFwd.apply(x)]
     out = None
@@ -70,6 +80,7 @@ def forward_sim_bf16(net, x, blocks):
         if conv.bias is not None:
             y = y + conv.bias.view(1, -1, 1, 1)
         y = r(y)                                                   # the engine stores the convolution output in bf16
+        y_conv = y
         nm = b.norm
         if isinstance(nm, nn.BatchNorm2d):
             use_batch = nm.training or (nm.running_mean is None and nm.running_var is None)
@@ -81,12 +92,13 @@ def forward_sim_bf16(net, x, blocks):
                 nm.num_batches_tracked += 1
         elif isinstance(nm, nn.InstanceNorm2d):
             y = F.instance_norm(y, None, None, nm.weight, nm.bias, True, 0.1, nm.eps)
+        m = masks[len(tensors) - 1] if masks is not None else None
         if b.act == 1:
-            y = F.relu(y)
+            y = F.relu(y) if m is None else _gate(y, m, 0.0)
         elif b.act == 2:
-            y = F.leaky_relu(y, b.slope)
+            y = F.leaky_relu(y, b.slope) if m is None else _gate(y, m, b.slope)
         elif b.act == 3:
-            y = F.prelu(y, b.prelu.weight)
+            y = F.prelu(y, b.prelu.weight) if m is None else _gate(y, m, b.prelu.weight)
         elif b.act == 4:
             y = torch.tanh(y)
         if b.residual is not None:
@@ -94,5 +106,7 @@ def forward_sim_bf16(net, x, blocks):
         y = r(y)
         if b.shuffle:
             y = F.pixel_shuffle(y, 2)
+        if capture is not None:
+            capture.append((y_conv.detach(), y.detach()))
         tensors.append(y)
     return out.squeeze() if type(net).__name__ == "Discriminator96" else out
