@@ -367,6 +367,15 @@ int ipr_hinge_d_loss_f32(const float *real_logits, const float *fake_logits, int
 /* Generator adversarial loss (models/dcgan.py:37-40): *loss = -mean(logits); dlogits (optional) = -1/batch. */
 int ipr_gen_adv_loss_f32(const float *logits, int batch, float loss_scale, float *loss, float *dlogits,
                          ipr_stream_t stream);
+/* Pointwise losses of the SRGAN / CycleGAN steps, value and gradient in one pass over x:
+ *   kind 0  mean (x-y)^2   (F.mse_loss, nn.MSELoss: models/srgan.py:49,59, models/cyclegan.py:122-143)
+ *   kind 1  mean |x-y|     (nn.L1Loss: models/cyclegan.py:125-133)
+ *   kind 2  mean BCE-with-logits (models/srgan.py:36-56)
+ * y == NULL: the target is the constant y0.  *loss = weight * mean(...), dx (optional) = weight * d mean / dx.
+ * Fixed-order two-stage reduction (deterministic). */
+size_t ipr_pointwise_loss_workspace_bytes(void);
+int ipr_pointwise_loss_f32(const float *x, const float *y, float y0, int64_t n, int kind, float weight, float *loss,
+                           float *dx, void *workspace, size_t workspace_bytes, ipr_stream_t stream);
 /* n standard-normal draws (Philox4x32-10 keyed by seed, Box-Muller); *counter (device) is the stream position and
  * advances by ceil(n/4) per launch, *ticket a zero-initialised device word: graph-replayable latent generation
  * replacing the host-side torch.randn + H2D copy of experiments/image_generation.py:94. */

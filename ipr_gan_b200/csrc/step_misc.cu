@@ -113,7 +113,72 @@ randn_kernel(float *__restrict__ out, long long n, unsigned long long seed, unsi
     }
 }
 
+// ---- pointwise losses of the SRGAN / CycleGAN steps, value and gradient in one pass
+//   kind 0: mean (x - y)^2        (F.mse_loss / nn.MSELoss: models/srgan.py:49,59, models/cyclegan.py:122-143)
+//   kind 1: mean |x - y|          (nn.L1Loss: models/cyclegan.py:125-133)
+//   kind 2: mean BCE-with-logits against the constant y0    (models/srgan.py:36-56)
+// y == nullptr: the target is the constant y0 (ones_like / zeros_like in the reference).
+// partial[cta] = sum of the per-element losses of that CTA's elements; dx = weight * dloss/dx.
+__global__ void __launch_bounds__(256)
+pointwise_loss_kernel(const float *__restrict__ x, const float *__restrict__ y, float y0, long long n, int kind, float weight,
+                      float *__restrict__ dx, float *__restrict__ partial)
+{
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
+    __shared__ float red[32];
+    const float gscale = weight / (float)n;
+    float acc = 0.0f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float xv = x[i], t = y ? y[i] : y0;
+        float l, g;
+        if (kind == 0) { const float d = xv - t; l = d * d; g = 2.0f * d; }
+        else if (kind == 1) { const float d = xv - t; l = fabsf(d); g = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f); }
+        else {
+            // max(x, 0) - x t + log(1 + exp(-|x|)); d/dx = sigmoid(x) - t
+            l = fmaxf(xv, 0.0f) - xv * t + log1pf(expf(-fabsf(xv)));
+            g = 1.0f / (1.0f + expf(-xv)) - t;
+        }
+        acc += l;
+        if (dx) dx[i] = g * gscale;
+    }
+    const float tot = ipr_block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256)
+pointwise_loss_finalize_kernel(const float *__restrict__ partial, int n_partial, float scale, float *__restrict__ loss)
+{
+    ipr_pdl_wait();
+    ipr_pdl_trigger();
+    __shared__ float red[32];
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < n_partial; i += blockDim.x) acc += partial[i];
+    const float tot = ipr_block_sum(acc, red);
+    if (threadIdx.x == 0) *loss = tot * scale;
+}
+
 }  // namespace
+
+extern "C" size_t ipr_pointwise_loss_workspace_bytes(void) { return (size_t)1024 * sizeof(float); }
+
+extern "C" int ipr_pointwise_loss_f32(const float *x, const float *y, float y0, int64_t n, int kind, float weight, float *loss,
+                                      float *dx, void *workspace, size_t workspace_bytes, ipr_stream_t stream)
+{
+    IPR_REQUIRE(x && loss && workspace, IPR_E_NULL);
+    IPR_REQUIRE(n > 0 && kind >= 0 && kind <= 2, IPR_E_SHAPE);
+    IPR_REQUIRE(workspace_bytes >= ipr_pointwise_loss_workspace_bytes(), IPR_E_WORKSPACE);
+    long long ctas = (n + 1023) / 1024;
+    if (ctas > 1024) ctas = 1024;
+    if (ctas > 2LL * ipr_sm_count()) ctas = 2LL * ipr_sm_count();
+    IPR_LAUNCH_PDL((pointwise_loss_kernel), (unsigned)ctas, 256, 0, ipr_cu(stream), x, y, y0, (long long)n, kind, weight, dx,
+                   (float *)workspace);
+    IPR_LAUNCH_CHECK();
+    IPR_LAUNCH_PDL((pointwise_loss_finalize_kernel), 1, 256, 0, ipr_cu(stream), (const float *)workspace, (int)ctas,
+                   weight / (float)n, loss);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
 
 extern "C" int ipr_hinge_d_loss_f32(const float *real_logits, const float *fake_logits, int batch, float loss_scale,
                                     float *losses, float *d_real, float *d_fake, ipr_stream_t stream)

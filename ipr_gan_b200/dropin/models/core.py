@@ -7,6 +7,21 @@ from abc import ABC, abstractmethod
 from collections import OrderedDict
 
 
+class Seeds(list):
+    """(tensor, gradient) pairs a fused step back-propagates from: every loss launch of this library returns the
+    loss value AND d(loss)/d(its input), so the backward pass starts at the networks' outputs -- the loss arithmetic
+    never becomes an autograd graph (``total.backward()`` of models/dcgan.py:76, models/wrappers.py:72,123)."""
+
+    def add(self, tensor, grad):
+        self.append((tensor, grad))
+
+    def backward(self):
+        import torch
+        if self:
+            torch.autograd.backward([t for t, _ in self], [g for _, g in self])
+        del self[:]
+
+
 class Model(ABC):
     def __init__(self):
         self._modules = OrderedDict()

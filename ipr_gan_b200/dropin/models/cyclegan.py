@@ -1,6 +1,10 @@
-"""CycleGAN step with the reference's interface (models/cyclegan.py:10-164): two generators, two PatchGAN
-discriminators, LSGAN + cycle + identity losses, image-history pools, linearly decaying learning rate;
-``_modules`` = GA, GB, DA, DB, optG, optD, schG, schD, poolA, poolB."""
+"""CycleGAN step behind the reference's interface (models/cyclegan.py:10-164): generators GA (A->B) and GB (B->A),
+PatchGAN discriminators DA / DB, LSGAN + cycle + identity losses, image-history pools, linearly decaying learning
+rate; ``_modules`` = GA, GB, DA, DB, optG, optD, schG, schD, poolA, poolB.
+
+Native step: the four networks run on ``ipr_gan_b200.seqnet``; the loss terms are rows of a table
+(name, kind, prediction, target, weight) evaluated by ``ops.pointwise_loss`` -- one launch per term giving the value
+and the gradient that seeds the backward pass (``models.core.Seeds``)."""
 from itertools import chain
 
 import torch
@@ -8,15 +12,15 @@ import torch.nn as nn
 from torch import optim
 
 import networks
-from models.core import Model
-from models.srgan import _make_opt
+from models.core import Model, Seeds
+from models.srgan import make_optimizer
 from models.util import Replica
 
 
 class ImagePool(nn.Module):
-    """History buffer of generated images kept as registered buffers so that it is checkpointed (models/util.py:5-35):
-    until full every image is stored and returned; afterwards each image is swapped with a random stored one with
-    probability 1/2."""
+    """History of generated images as registered buffers, so that it is part of the checkpoint (models/util.py:5-35).
+    While filling up, images pass through and are stored; once full, each incoming image is exchanged with a random
+    stored one with probability 1/2 (the CPU RNG draws ``rand`` then ``randperm``, in that order)."""
 
     def __init__(self, pool_size):
         super().__init__()
@@ -25,113 +29,138 @@ class ImagePool(nn.Module):
             self.register_buffer("images", torch.tensor([]))
             self.register_buffer("counts", torch.zeros([]))
 
-    def load_state_dict(self, *args, **kwargs):
-        self.images = torch.empty_like(args[0]["images"])
-        super().load_state_dict(*args, **kwargs)
+    def load_state_dict(self, state, *args, **kwargs):
+        self.images = torch.empty_like(state["images"])           # the stored history decides the buffer's shape
+        return super().load_state_dict(state, *args, **kwargs)
 
-    def __call__(self, images):
-        if self.pool_size <= 0:
-            return images.detach()
-        if self.counts < self.pool_size:
-            self.images = torch.cat([self.images.to(images.device), images.detach()], dim=0)[:self.pool_size]
-            self.counts += images.size(0)
-            return images.detach()
+    def forward(self, images):
         images = images.detach()
-        swap = torch.rand(images.size(0)) > 0.5
-        slot = torch.randperm(self.pool_size)[:images.size(0)]
-        old = self.images[slot[swap]].clone()
-        self.images[slot[swap]] = images[swap].detach()
-        images[swap] = old
-        return images.detach()
+        if self.pool_size <= 0:
+            return images
+        n = images.size(0)
+        if self.counts < self.pool_size:
+            self.images = torch.cat([self.images.to(images.device), images])[:self.pool_size]
+            self.counts += n
+            return images
+        take = torch.rand(n) > 0.5
+        where = torch.randperm(self.pool_size)[:n][take]
+        out = images.clone()
+        out[take] = self.images[where]
+        self.images[where] = images[take]
+        return out
 
 
 class CycleGAN(Model):
+    seeded = True                        # wrappers add (tensor, gradient) seeds instead of loss-graph terms
+
     def __init__(self, config, device=[torch.device("cpu"), ]):
         super().__init__()
         self.device = device
         ids = [d.index for d in device]
-
-        def net(name):
-            return Replica(getattr(networks, name)().to(device[0]), device_ids=ids)
-
-        self.GA, self.GB = net(config.G), net(config.G)
-        self.DA, self.DB = net(config.D), net(config.D)
+        for name, key in (("GA", config.G), ("GB", config.G), ("DA", config.D), ("DB", config.D)):
+            net = Replica(getattr(networks, key)().to(device[0]), device_ids=ids)
+            net.train()
+            setattr(self, name, net)
         self.poolA, self.poolB = ImagePool(config.pool_size), ImagePool(config.pool_size)
-        for m in (self.GA, self.GB, self.DA, self.DB):
-            m.train()
         self.lambda_A, self.lambda_B, self.lambda_idt = config.lambda_A, config.lambda_B, config.lambda_idt
-        self.optG = _make_opt(config, list(chain(self.GA.parameters(), self.GB.parameters())), device[0])
-        self.optD = _make_opt(config, list(chain(self.DA.parameters(), self.DB.parameters())), device[0])
+        self.optG = make_optimizer(config, list(chain(self.GA.parameters(), self.GB.parameters())), device[0])
+        self.optD = make_optimizer(config, list(chain(self.DA.parameters(), self.DB.parameters())), device[0])
         half = config.epoch // 2
-        decay = lambda e: 1.0 - max(0, e - half) / half                                   # noqa: E731
+
+        def decay(epoch):                                   # models/cyclegan.py:52-59
+            return 1.0 - max(0, epoch - half) / half
         self.schedulerG = optim.lr_scheduler.LambdaLR(self.optG, lr_lambda=decay)
         self.schedulerD = optim.lr_scheduler.LambdaLR(self.optD, lr_lambda=decay)
-        self.MSE, self.L1 = nn.MSELoss(), nn.L1Loss()
         self._modules.update(GA=self.GA, GB=self.GB, DA=self.DA, DB=self.DB, optG=self.optG, optD=self.optD,
                              schG=self.schedulerG, schD=self.schedulerD, poolA=self.poolA, poolB=self.poolB)
+        self.g_seeds = Seeds()
+        self._scalars = {}               # metric name -> (0-dim device tensor, factor applied on the host)
 
-    def get_metrics(self):
-        names = ("G/A", "G/B", "G/CycA", "G/CycB", "G/IdtA", "G/IdtB", "G/Sum", "D/RealA", "D/FakeA", "D/SumA",
-                 "D/RealB", "D/FakeB", "D/SumB")
-        ts = (self.LossGA, self.LossGB, self.LossCycA, self.LossCycB, self.LossIdtA, self.LossIdtB, self.LossG,
-              self.LossDRA, self.LossDFA, self.LossDA, self.LossDRB, self.LossDFB, self.LossDB)
-        dev = self.LossG.device
-        out = dict(zip(names, torch.stack([t.detach().to(dev).float() for t in ts]).tolist()))
-        out["LR"] = self.optG.param_groups[0]["lr"]
-        return out
+    def _terms(self, rows, seeds):
+        """rows: (metric name, kind, prediction, target, gradient weight, reported = value * factor)"""
+        from ipr_gan_b200 import ops
+        for name, kind, pred, target, weight, report in rows:
+            value, grad = ops.pointwise_loss(kind, pred, target, weight)
+            self._scalars[name] = (value, report)
+            seeds.add(pred, grad)
 
+    # ---- generator step (models/cyclegan.py:91-105, 122-143)
     def forward_g(self, data):
         self.real_A, self.real_B = data["real_A"], data["real_B"]
         self.fake_B, self.fake_A = self.GA(self.real_A), self.GB(self.real_B)
         self.rec_A, self.rec_B = self.GB(self.fake_B), self.GA(self.fake_A)
         self.idt_A, self.idt_B = self.GA(self.real_B), self.GB(self.real_A)
-        self.GA_logits, self.GB_logits = self.DA(self.fake_B), self.DB(self.fake_A)
+        for d in (self.DA, self.DB):                       # only dD/d(image) is used in this step
+            d.module._ipr_skip_param_grads = True
+        try:
+            self.GA_logits, self.GB_logits = self.DA(self.fake_B), self.DB(self.fake_A)
+        finally:
+            for d in (self.DA, self.DB):
+                d.module._ipr_skip_param_grads = False
 
+    def compute_g_loss(self):
+        dev = self.rec_A.device
+        self.real_A = self.real_A.to(dev, non_blocking=True)
+        self.real_B = self.real_B.to(dev, non_blocking=True)
+        la, lb, li = self.lambda_A, self.lambda_B, self.lambda_idt
+        self.g_seeds = Seeds()
+        rows = [("G/A", "mse", self.GA_logits, 1.0, 1.0, 1.0), ("G/B", "mse", self.GB_logits, 1.0, 1.0, 1.0),
+                ("G/CycA", "l1", self.rec_A, self.real_A, la, 1.0), ("G/CycB", "l1", self.rec_B, self.real_B, lb, 1.0)]
+        if li > 0:
+            # the identity terms enter the total with lambda_idt but are reported without it (models/cyclegan.py:135-141)
+            rows += [("G/IdtA", "l1", self.idt_A, self.real_B, lb * li, 1.0 / li),
+                     ("G/IdtB", "l1", self.idt_B, self.real_A, la * li, 1.0 / li)]
+        self._terms(rows, self.g_seeds)
+        total = None
+        for name, *_ in rows:
+            v = self._scalars[name][0]
+            total = v if total is None else total + v
+        self.LossG = total                                  # the weighted sum that is minimised
+        self.LossGA, self.LossGB = self._scalars["G/A"][0], self._scalars["G/B"][0]
+
+    def backward_g(self, extra=None):
+        self.optG.zero_grad()
+        self.g_seeds.backward()
+
+    def update_g(self, data, update=True):
+        self.forward_g(data)
+        self.compute_g_loss()
+        if update:
+            self.backward_g()
+            self.optG.step()
+
+    # ---- discriminator step (models/cyclegan.py:107-120, 145-164)
     def forward_d(self, data):
         self.real_A, self.real_B = data["real_A"], data["real_B"]
         self.fake_A, self.fake_B = self.poolA(data["fake_A"]), self.poolB(data["fake_B"])
         self.RA_logits, self.FA_logits = self.DB(self.real_A), self.DB(self.fake_A.detach())
         self.RB_logits, self.FB_logits = self.DA(self.real_B), self.DA(self.fake_B.detach())
 
-    def compute_g_loss(self):
-        self.real_A = self.real_A.to(self.rec_A.device)
-        self.real_B = self.real_B.to(self.rec_B.device)
-        self.LossGA = self.MSE(self.GA_logits, torch.ones_like(self.GA_logits))
-        self.LossGB = self.MSE(self.GB_logits, torch.ones_like(self.GB_logits))
-        self.LossCycA = self.L1(self.rec_A, self.real_A) * self.lambda_A
-        self.LossCycB = self.L1(self.rec_B, self.real_B) * self.lambda_B
-        self.LossG = self.LossGA + self.LossGB + self.LossCycA + self.LossCycB
-        if self.lambda_idt > 0:
-            self.LossIdtA = self.L1(self.idt_A, self.real_B) * self.lambda_B
-            self.LossIdtB = self.L1(self.idt_B, self.real_A) * self.lambda_A
-            self.LossG = self.LossG + self.lambda_idt * (self.LossIdtA + self.LossIdtB)
-        else:
-            self.LossIdtA = self.LossIdtB = torch.zeros([])
-
     def compute_d_loss(self):
-        self.LossDRA = self.MSE(self.RB_logits, torch.ones_like(self.RB_logits))
-        self.LossDFA = self.MSE(self.FB_logits, torch.zeros_like(self.FB_logits))
-        self.LossDA = (self.LossDRA + self.LossDFA) * 0.5
-        self.LossDRB = self.MSE(self.RA_logits, torch.ones_like(self.RA_logits))
-        self.LossDFB = self.MSE(self.FA_logits, torch.zeros_like(self.FA_logits))
-        self.LossDB = (self.LossDRB + self.LossDFB) * 0.5
-
-    def update_lr(self):
-        self.schedulerG.step()
-        self.schedulerD.step()
-
-    def update_g(self, data, update=True):
-        self.forward_g(data)
-        self.compute_g_loss()
-        if update:
-            self.optG.zero_grad()
-            self.LossG.backward()
-            self.optG.step()
+        self._d_seeds = Seeds()
+        # each discriminator minimises half the sum of its two terms; the terms are reported un-halved
+        self._terms([("D/RealA", "mse", self.RB_logits, 1.0, 0.5, 2.0), ("D/FakeA", "mse", self.FB_logits, 0.0, 0.5, 2.0),
+                     ("D/RealB", "mse", self.RA_logits, 1.0, 0.5, 2.0), ("D/FakeB", "mse", self.FA_logits, 0.0, 0.5, 2.0)],
+                    self._d_seeds)
 
     def update_d(self, data):
         self.forward_d(data)
         self.compute_d_loss()
         self.optD.zero_grad()
-        self.LossDA.backward()
-        self.LossDB.backward()
+        self._d_seeds.backward()
         self.optD.step()
+
+    def update_lr(self):
+        self.schedulerG.step()
+        self.schedulerD.step()
+
+    def get_metrics(self):
+        names = sorted(self._scalars)
+        vals = torch.stack([self._scalars[n][0] for n in names]).tolist()          # one device-to-host copy
+        m = {n: v * self._scalars[n][1] for n, v in zip(names, vals)}
+        idt_a, idt_b = m.get("G/IdtA", 0.0), m.get("G/IdtB", 0.0)
+        return {"G/A": m["G/A"], "G/B": m["G/B"], "G/CycA": m["G/CycA"], "G/CycB": m["G/CycB"], "G/IdtA": idt_a,
+                "G/IdtB": idt_b, "G/Sum": m["G/A"] + m["G/B"] + m["G/CycA"] + m["G/CycB"] + self.lambda_idt * (idt_a + idt_b),
+                "D/RealA": m["D/RealA"], "D/FakeA": m["D/FakeA"], "D/SumA": 0.5 * (m["D/RealA"] + m["D/FakeA"]),
+                "D/RealB": m["D/RealB"], "D/FakeB": m["D/FakeB"], "D/SumB": 0.5 * (m["D/RealB"] + m["D/FakeB"]),
+                "LR": self.optG.param_groups[0]["lr"]}

@@ -76,6 +76,7 @@ class DCGAN(Model):
                 isinstance(self.D.module, networks.SNDiscriminator):
             self.board = MetricsBoard(self.optD.arena, self.optG.arena)
             self.optD.arena.track_clean = self.optG.arena.track_clean = True
+        self.seeded = self.board is not None
         self.g_seeds = []                # (tensor, gradient) pairs the generator step back-propagates from
 
     # ---- losses (models/dcgan.py:31-40)

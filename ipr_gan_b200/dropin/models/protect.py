@@ -36,31 +36,39 @@ class BlackBoxWrapper(Wrapper):
         self._modules["fn_out"] = self.fn_out
 
     def _fused(self):
-        """The inner model's metrics board when the whole generator step runs on the fused path (native DCGAN
-        networks + SSIM watermark loss); None otherwise (`board` falls through the wrappers, None when absent)."""
+        """True when the wrapped model back-propagates from seed gradients (``seeded``: the native DCGAN / SRGAN /
+        CycleGAN steps) and the watermark loss is SSIM: forward + backward of the loss are then ONE launch."""
+        return bool(self.seeded) and self.config.loss_fn == "ssim"
+
+    def _wm_slot(self):
+        """(1-element view the loss value is written to, scale): the inner model's metrics board when it has one."""
         board = self.board
-        return board if board is not None and self.config.loss_fn == "ssim" else None
+        if board is not None:
+            return board.slot(board.P_WM), board.loss_scale
+        if getattr(self, "_w_slot", None) is None:
+            self._w_slot = torch.zeros(1, device=self.device[0])
+        return self._w_slot, 1.0
 
     def compute_g_loss(self):
         self.LossG = self.model.LossG
-        board = self._fused()
-        if board is not None:
+        if self._fused():
+            slot, scale = self._wm_slot()
             if self.inhibit:
-                board.slot(board.P_WM).zero_()
+                slot.zero_()
             else:
-                # forward + backward of the SSIM loss in one launch: the scalar goes to its board slot, lambda * dLoss/dx
+                # forward + backward of the SSIM loss in one launch: the scalar goes to its slot, lambda * dLoss/dx
                 # becomes the seed gradient of the trigger pass (no autograd node, no multiply by grad_output)
                 from ipr_gan_b200 import ops
                 _, dx = ops.ssim_loss_fwd_bwd(self.Gxwm.detach(), self.ywm, self.config.normalized, grad_scale=self.Lambda,
-                                              loss_out=board.slot(board.P_WM), loss_scale=board.loss_scale)
+                                              loss_out=slot, loss_scale=scale)
                 self.g_seeds.append((self.Gxwm, dx))
-            self.LossW = board.scalar(board.P_WM)
+            self.LossW = slot[0]
             return
         if self.inhibit:
             self.LossW = torch.zeros_like(self.LossG)
         else:
             self.LossW = self.loss_fn(self.Gxwm, self.ywm)
-            if self.board is not None:       # fused inner model, other loss (l1 / mse): lambda * dLossW seeds the backward
+            if self.seeded:                  # seeded inner model, other loss (l1 / mse): lambda * dLossW seeds the backward
                 self.g_seeds.append((self.LossW, torch.full_like(self.LossW, float(self.Lambda))))
 
     def _triggers(self, source, produced):
@@ -108,7 +116,7 @@ class BlackBoxWrapper(Wrapper):
     def get_metrics(self):
         metrics = self.model.get_metrics()
         if not self.inhibit:
-            board = self._fused()
+            board = self.board if self._fused() else None
             w = board.fetch()[board.P_WM] if board is not None else self.LossW.item()
             metrics[f"P/{self.config.loss_fn.upper()}"] = w
             metrics["G/Sum"] += self.Lambda * w
@@ -148,7 +156,7 @@ def _backward_and_step(wrapper, total):
     backward starts from the seed gradients the loss launches produced (`backward_g` of the innermost model)."""
     backward_g = wrapper.backward_g               # falls through to the wrapped model; None for other model types
     if backward_g is not None:
-        backward_g(None if wrapper.board is not None else total())
+        backward_g(None if wrapper.seeded else total())
     else:
         wrapper.model.optG.zero_grad()
         total().backward()

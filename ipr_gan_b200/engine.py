@@ -161,7 +161,13 @@ class PackSet(object):
     gather launch (csrc/optim.cu) whenever the masters changed."""
 
     def __init__(self, module, specs, specs_f32=()):
-        self.arena = flat.arena_for(list(module.parameters()))
+        # the arena the parameters already live in (an optimizer may have built one spanning several networks, e.g.
+        # CycleGAN's optG over both generators), else one for this network alone
+        params = list(module.parameters())
+        arena = flat.arena_of(params[0])
+        if arena is None or any(flat.arena_of(p) is not arena for p in params):
+            arena = flat.arena_for(params)
+        self.arena = arena
         dev = self.arena.param.device
         # fp32 side table: permuted fp32 copies (Linear bias in NHWC feature order, the final GEMV row), same launch
         parts32, self.slices32, off32 = [], {}, 0

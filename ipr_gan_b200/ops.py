@@ -223,6 +223,27 @@ def gen_adv_loss(logits, slot, loss_scale=1.0):
     return d
 
 
+_LOSS_KINDS = {"mse": 0, "l1": 1, "bce_logits": 2}
+
+
+def pointwise_loss(kind, x, target, weight=1.0, need_grad=True):
+    """-> (weight * loss 0-dim, weight * dloss/dx or None) in one pass (csrc/step_misc.cu).  ``target``: a tensor of
+    x's shape, or a Python number (the reference's ones_like / zeros_like targets)."""
+    x = _req(x, "x")
+    const = not isinstance(target, torch.Tensor)
+    y = None if const else _req(target, "target")
+    if y is not None and y.numel() != x.numel():
+        raise IprError("pointwise loss: target shape mismatch")
+    loss = torch.empty((), device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x) if need_grad else None
+    nbytes = lib().ipr_pointwise_loss_workspace_bytes()
+    ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+    check(lib().ipr_pointwise_loss_f32(_p(x), _p(y) if y is not None else None, float(target) if const else 0.0, x.numel(),
+                                       _LOSS_KINDS[kind], float(weight), _p(loss), _p(dx) if need_grad else None, _p(ws),
+                                       nbytes, _stream()), "ipr_pointwise_loss_f32")
+    return loss, dx
+
+
 class DeviceNormal(object):
     """Standard-normal draws made on the device (Philox4x32-10 keyed by ``seed``; the stream position lives in
     device memory and advances with every launch, so a captured CUDA graph draws fresh latents on every replay)."""

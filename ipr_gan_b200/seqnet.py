@@ -319,6 +319,7 @@ class _SeqFn(torch.autograd.Function):
             tensors.append(z)
         ctx.net, ctx.tape, ctx.out = net, tape, out
         ctx.x_needs_grad = x.requires_grad
+        ctx.skip_params = bool(getattr(net, "_ipr_skip_param_grads", False))
         ctx.in_shape = (N, C, H, W)
         return out
 
@@ -329,6 +330,8 @@ class _SeqFn(torch.autograd.Function):
         dev = dout.device
         grads = [None] * len(P.params)
         hook = getattr(net, "_ipr_sign_hook", None)
+        # a pass whose parameter gradients are never used (a discriminator inside a generator step): data gradient only
+        skip_params = ctx.skip_params
 
         def give(param, value_fn):
             """Weight-type gradient: accumulate into the bound ``.grad`` view when there is one, else return a tensor."""
@@ -362,28 +365,34 @@ class _SeqFn(torch.autograd.Function):
                 if rec["has_norm"] == 2:
                     raise RuntimeError("seqnet: backward through eval-mode BatchNorm is not on the training path")
                 # parameter gradients of this launch land in fresh buffers and are handed over below
-                dg = torch.empty_like(gamma) if gamma is not None else None
-                db = torch.empty_like(gamma) if gamma is not None else None
+                if skip_params:
+                    gamma_g = None
+                else:
+                    gamma_g = gamma
+                dg = torch.empty_like(gamma) if gamma_g is not None else None
+                db = torch.empty_like(gamma) if gamma_g is not None else None
                 sg, g0, sc = (None, 0.0, 0.0)
-                if hook is not None and gamma is not None:
+                if hook is not None and gamma_g is not None:
                     # white-box sign loss (tools/sign_model.py:42-49): d/dgamma is added inside this launch, once per
                     # armed step and layer (models/protect.py: _SignHook)
                     sg, g0, sc = hook(P.norm_index[id(nm)])
                 slope_ptr = b.prelu.weight.detach() if b.prelu is not None else None
-                dsl = torch.empty_like(slope_ptr) if slope_ptr is not None else None
+                dsl = torch.empty_like(slope_ptr) if (slope_ptr is not None and not skip_params) else None
                 check(lib().ipr_norm_bwd_bf16(_p(dz), _p(y0), _p(dy0), rec["groups"], rec["rows"], b.n_p,
                                               rec["has_norm"], _p(gamma), _p(rec["scale"]), _p(rec["shift"]),
                                               _p(rec["mean"]), _p(rec["rstd"]), _p(dg), _p(db), 0, _p(sg), float(g0),
                                               float(sc), b.act, float(b.slope), _p(slope_ptr), _p(dsl), _p(ws), nbytes,
                                               _st()), "ipr_norm_bwd_bf16")
-                if gamma is not None:
+                if gamma_g is not None:
                     give(nm.weight, lambda dst, acc, v=dg: dst.add_(v) if acc else dst.copy_(v))
                     give(nm.bias, lambda dst, acc, v=db: dst.add_(v) if acc else dst.copy_(v))
                 if dsl is not None:
                     give(b.prelu.weight, lambda dst, acc, v=dsl: dst.add_(v) if acc else dst.copy_(v))
             dy2 = dy0.view(M, 1, 1, b.n_p)
             # bias and weight gradients
-            if b.conv.bias is not None:
+            if skip_params:
+                pass
+            elif b.conv.bias is not None:
                 def _bias(dst, acc, dy2=dy2, b=b):
                     full = engine.colsum_bf16(dy2.view(M, b.n_p))
                     if acc:
@@ -391,8 +400,9 @@ class _SeqFn(torch.autograd.Function):
                     else:
                         dst.copy_(full[:b.cout])
                 give(b.conv.bias, _bias)
-            give(b.conv.weight, lambda dst, acc, dy2=dy2, rec=rec, b=b: b.wg_plan.run(dy2, rec["col"].view(M, 1, 1, b.kp), dst,
-                                                                                      accumulate=acc))
+            if not skip_params:
+                give(b.conv.weight, lambda dst, acc, dy2=dy2, rec=rec, b=b: b.wg_plan.run(dy2, rec["col"].view(M, 1, 1, b.kp), dst,
+                                                                                          accumulate=acc))
             # data gradient
             need_dx = i > 0 or ctx.x_needs_grad
             if need_dx:
