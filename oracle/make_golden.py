@@ -255,7 +255,56 @@ def gen_srgan_cyclegan_steps(ref):
     np.savez_compressed(os.path.join(GOLD, "srgan_cyclegan_steps.npz"), **out)
 
 
+def gen_srgan_cyclegan_baseline_shapes(ref):
+    """The same protected steps at the BASELINE.json shapes: config 3 = SRGAN 24 -> 96 at batch 16 (noise patch 12,
+    watermark 48), config 4 = CycleGAN Resnet9Blocks at 128 x 128, batch 1, patch / watermark 64
+    (configs/SRGAN/complete/srgan-imagenet-a.yaml, configs/CycleGAN/complete/cyclegan-city-a.yaml)."""
+    import torchvision
+    models, Config = ref["models"], ref["configs"].Config
+    import networks.vgg as ref_vgg
+    ref_vgg.vgg19 = lambda pretrained=True: torchvision.models.vgg19(weights=None)
+    out = {}
+    torch.manual_seed(SEED)
+    sr = models.SRGAN(Config({"G": "SRResNet", "D": "Discriminator96", "V": "VGG19Feature", "opt": "Adam",
+                              "opt_param": {"lr": 1.0e-4, "betas": [0.9, 0.999]}, "type": "SRGAN"}), device=[torch.device("cpu")])
+    sr = _wrap(models, Config, sr,
+               {"fn_inp": {"type": "RandomNoisePatch", "size": 12}, "fn_out": {"size": 48, "opaque": True, "type": "PasteWatermark",
+                                                                              "watermark": MARK},
+                "lambda": 1.0, "loss_fn": "ssim", "normalized": False, "input_var": "low_res", "output_var": "super_res",
+                "target": "G"},
+               {"gamma_0": 0.1, "string": "EXAMPLE A", "target": "G"})
+    g = torch.Generator().manual_seed(SEED + 1)
+    lr, hr = torch.rand(16, 3, 24, 24, generator=g), torch.rand(16, 3, 96, 96, generator=g)
+    sr.update_g({"low_res": lr, "high_res": hr, "pretrain": False})
+    sr.update_d({"high_res": sr.high_res, "super_res": sr.super_res})
+    m = sr.get_metrics()
+    out["sr_keys"], out["sr"] = np.array(sorted(m)), np.array([m[k] for k in sorted(m)])
+    out["sr_super_res"] = t2n(sr.super_res[:2, :, 40:56, 40:56])
+    torch.manual_seed(SEED)
+    cg = models.CycleGAN(Config({"G": "Resnet9Blocks", "D": "ConvDiscriminator", "lambda_A": 10.0, "lambda_B": 10.0,
+                                 "lambda_idt": 0.5, "opt": "Adam", "opt_param": {"lr": 2.0e-4, "betas": [0.5, 0.999]},
+                                 "pool_size": 50, "epoch": 200, "type": "CycleGAN"}), device=[torch.device("cpu")])
+    cg = _wrap(models, Config, cg,
+               {"fn_inp": {"type": "RandomNoisePatch", "size": 64}, "fn_out": {"size": 64, "opaque": True, "type": "PasteWatermark",
+                                                                              "watermark": MARK},
+                "lambda": 1.0, "loss_fn": "ssim", "normalized": True, "input_var": "real_B", "output_var": "fake_A",
+                "target": "GB"},
+               {"gamma_0": 0.1, "string": "EXAMPLE A", "target": "GB"})
+    a, b = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1, torch.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    cg.update_g({"real_A": a, "real_B": b})
+    cg.update_d({"real_A": cg.real_A, "real_B": cg.real_B, "fake_A": cg.fake_A.detach(), "fake_B": cg.fake_B.detach()})
+    m2 = cg.get_metrics()
+    out["cg_keys"], out["cg"] = np.array(sorted(m2)), np.array([m2[k] for k in sorted(m2)])
+    out["cg_fake_A"] = t2n(cg.fake_A[:1, :, 56:72, 56:72])
+    np.savez_compressed(os.path.join(GOLD, "srgan_cyclegan_baseline_shapes.npz"), **out)
+
+
 def main():
+    if "--baseline-shapes-only" in sys.argv:
+        torch.set_num_threads(1)
+        with ref_bridge.reference_modules() as ref:
+            gen_srgan_cyclegan_baseline_shapes(ref)
+        return
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)  # summation order of CPU reductions must not depend on the thread count
     with ref_bridge.reference_modules() as ref:
@@ -265,6 +314,7 @@ def main():
         gen_phash(ref)
         gen_dcgan_step(ref)
         gen_srgan_cyclegan_steps(ref)
+        gen_srgan_cyclegan_baseline_shapes(ref)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 
