@@ -34,9 +34,11 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-eager-baseline", action="store_true")
     ap.add_argument("--device-latents", action="store_true", help="draw latents on the device instead of copying them")
-    ap.add_argument("--workload", default="step", choices=["step", "verify"],
+    ap.add_argument("--workload", default="step", choices=["step", "verify", "srgan", "cyclegan"],
                     help="step: the protected training step (the metric); verify: BASELINE config 5, the watermark / "
-                         "signature verification sweep over 10 000 trigger samples, sharded over the ranks")
+                         "signature verification sweep over 10 000 trigger samples, sharded over the ranks; srgan / "
+                         "cyclegan: BASELINE configs 3 / 4, one protected step of IPR-SRGAN (batch 16, 24 -> 96) / "
+                         "IPR-CycleGAN (batch 1, 128 x 128) on the native networks (single GPU)")
     ap.add_argument("--samples", type=int, default=10000, help="--workload verify: trigger samples in the sweep")
     return ap.parse_args()
 
@@ -471,6 +473,80 @@ def run_verify(args):
     _finish(world)
 
 
+def run_family(args):
+    """BASELINE configs 3 / 4: one protected training step of IPR-SRGAN (experiments/image_super_resolution.py:84-113) or
+    IPR-CycleGAN (experiments/image_translation.py:90-112) through the drop-in models, networks on the native engine."""
+    import torch
+    import ipr_gan_b200
+    ipr_gan_b200.enable_dropin()
+    import models
+    from configs import Config
+    from configs.presets import WATERMARK_A
+    from ipr_gan_b200 import _lib
+    os.environ.setdefault("IPR_VGG_RANDOM_INIT", "1")          # no network: seeded random VGG weights (outside the path)
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(1234)
+    gen = torch.Generator().manual_seed(1234)
+    if args.workload == "srgan":
+        m = models.SRGAN(Config({"G": "SRResNet", "D": "Discriminator96", "V": "VGG19Feature", "opt": "Adam",
+                                 "opt_param": {"lr": 1.0e-4, "betas": [0.9, 0.999]}, "type": "SRGAN"}), device=[dev])
+        m = models.BlackBoxWrapper(m, Config({"fn_inp": {"type": "RandomNoisePatch", "size": 12},
+                                              "fn_out": {"size": 48, "opaque": True, "type": "PasteWatermark", "watermark": WATERMARK_A},
+                                              "lambda": 1.0, "loss_fn": "ssim", "normalized": False, "input_var": "low_res",
+                                              "output_var": "super_res", "target": "G"}))
+        m = models.WhiteBoxWrapper(m, Config({"gamma_0": 0.1, "string": "EXAMPLE A", "target": "G"}))
+        lr_h, hr_h = torch.rand(16, 3, 24, 24, generator=gen).pin_memory(), torch.rand(16, 3, 96, 96, generator=gen).pin_memory()
+
+        def step():
+            m.update_g({"low_res": lr_h.to(dev, non_blocking=True), "high_res": hr_h.to(dev, non_blocking=True), "pretrain": False})
+            m.update_d({"high_res": m.high_res, "super_res": m.super_res})
+            return m.get_metrics()
+        name, h2d = "IPR-SRGAN 24->96 protected step, batch 16 (SRResNet + Discriminator96 + VGG content loss)", (lr_h.numel() + hr_h.numel()) * 4
+    else:
+        m = models.CycleGAN(Config({"G": "Resnet9Blocks", "D": "ConvDiscriminator", "lambda_A": 10.0, "lambda_B": 10.0,
+                                    "lambda_idt": 0.5, "opt": "Adam", "opt_param": {"lr": 2.0e-4, "betas": [0.5, 0.999]},
+                                    "pool_size": 50, "epoch": 200, "type": "CycleGAN"}), device=[dev])
+        m = models.BlackBoxWrapper(m, Config({"fn_inp": {"type": "RandomNoisePatch", "size": 64},
+                                              "fn_out": {"size": 64, "opaque": True, "type": "PasteWatermark", "watermark": WATERMARK_A},
+                                              "lambda": 1.0, "loss_fn": "ssim", "normalized": True, "input_var": "real_B",
+                                              "output_var": "fake_A", "target": "GB"}))
+        m = models.WhiteBoxWrapper(m, Config({"gamma_0": 0.1, "string": "EXAMPLE A", "target": "GB"}))
+        a_h = (torch.rand(1, 3, 128, 128, generator=gen) * 2 - 1).pin_memory()
+        b_h = (torch.rand(1, 3, 128, 128, generator=gen) * 2 - 1).pin_memory()
+
+        def step():
+            m.update_g({"real_A": a_h.to(dev, non_blocking=True), "real_B": b_h.to(dev, non_blocking=True)})
+            m.update_d({"real_A": m.real_A, "real_B": m.real_B, "fake_A": m.fake_A.detach(), "fake_B": m.fake_B.detach()})
+            return m.get_metrics()
+        name, h2d = "IPR-CycleGAN 128x128 protected step, batch 1 (Resnet9Blocks x2 + PatchGAN x2, InstanceNorm sign loss)", (a_h.numel() + b_h.numel()) * 4
+    for _ in range(max(3, args.warmup)):
+        last = step()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    total, before = 0.0, _lib.launch_count()
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        last = step()
+        b.record()
+        torch.cuda.synchronize()
+        total += a.elapsed_time(b)
+    launches = _lib.launch_count() - before
+    ms = total / args.steps
+    print(json.dumps({"metric": name + ", steps/sec", "value": 1e3 / ms, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": name, "l2": "flushed between steps", "timing": "CUDA events around each eager step, host "
+                                 "batch in / metrics out inside the timed region (so value == e2e)"},
+                      "clocks": sampler.stop(), "gpu_launches": int(launches),
+                      "e2e": {"value": 1e3 / ms, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 64},
+                      "last_metrics": last}))
+
+
 def _finish(world):
     """Leave without tearing NCCL down: destroying a process group whose collectives live inside a captured CUDA
     graph can block at exit; the ranks just synchronise and exit."""
@@ -488,5 +564,7 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.workload == "verify":
         run_verify(a)
+    elif a.workload in ("srgan", "cyclegan"):
+        run_family(a)
     else:
         run_b200(a)
