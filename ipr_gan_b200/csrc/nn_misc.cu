@@ -29,6 +29,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+__device__ __forceinline__ void ldg8(const float *p, float (&f)[8]) {      // p 16-byte aligned (channel index % 8 == 0)
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 // ------------------------------------------------------------------------------------ im2col3
 // out[(n,h,w)][k], k = (kh*3+kw)*3 + c  <-  x[n, c, h+kh-1, w+kw-1] (zero outside), k in [27,32) = 0: 64-byte rows.
 // The GEMMs read them through 64-channel TMA boxes whose upper half is out-of-bounds zero fill.
@@ -129,10 +134,12 @@ bn_apply_relu_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, const f
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
         const int c0 = (int)(i % c_vec) * 8;
-        float f[8];
+        float f[8], sc[8], sh[8];
         unpack8(__ldg(x + i), f);
+        ldg8(scale + c0, sc);
+        ldg8(shift + c0, sh);
 #pragma unroll
-        for (int k = 0; k < 8; k++) f[k] = fmaxf(fmaf(f[k], __ldg(scale + c0 + k), __ldg(shift + c0 + k)), 0.0f);
+        for (int k = 0; k < 8; k++) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.0f);
         y[i] = pack8(f);
     }
 }
@@ -238,13 +245,15 @@ bn_bwd_apply_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ xraw
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
         const int c0 = (int)(i % c_vec) * 8;
-        float d[8], xv[8], o[8];
+        float d[8], xv[8], o[8], sc[8], sh[8], ca[8], cb[8], cd[8];
         unpack8(__ldg(dy + i), d);
         unpack8(__ldg(xraw + i), xv);
+        ldg8(scale + c0, sc); ldg8(shift + c0, sh);
+        ldg8(coef + c0, ca); ldg8(coef + C + c0, cb); ldg8(coef + 2 * C + c0, cd);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const float g = fmaf(xv[k], __ldg(scale + c0 + k), __ldg(shift + c0 + k)) > 0.0f ? d[k] : 0.0f;
-            o[k] = __ldg(coef + c0 + k) * g + __ldg(coef + C + c0 + k) * xv[k] + __ldg(coef + 2 * C + c0 + k);
+            const float g = fmaf(xv[k], sc[k], sh[k]) > 0.0f ? d[k] : 0.0f;
+            o[k] = ca[k] * g + cb[k] * xv[k] + cd[k];
         }
         dx[i] = pack8(o);
     }
@@ -563,10 +572,19 @@ colsum_stage2(const float *__restrict__ in, int rows, int ncols, float *__restri
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
+    // 32 columns x 8 row lanes per CTA (the first version walked the rows with ONE thread per column: 10 us of pure
+    // load latency per launch, 20 launches per step); fixed order: lane partials, then lanes 0..7
+    __shared__ double sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     double acc = 0.0;
-    for (int r = 0; r < rows; r++) acc += (double)in[(size_t)r * ncols + c];
+    if (c < ncols)
+        for (int r = ty; r < rows; r += 8) acc += (double)in[(size_t)r * ncols + c];
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty != 0 || c >= ncols) return;
+#pragma unroll
+    for (int y = 1; y < 8; y++) acc += sm[y][tx];
     const float v = (float)acc * scale;
     const int o = out_index ? __ldg(out_index + c) : c;
     if (accumulate == 2) atomicAdd(out + o, v);                   // two-contribution accumulation across streams
@@ -616,7 +634,7 @@ extern "C" int ipr_colsum_partials_f32(const float *partial, int rows, int ncols
     dim3 grid((ncols + 31) / 32, G);
     IPR_LAUNCH_PDL((colsum_partials_stage1), grid, 256, 0, ipr_cu(stream), partial, rows, ncols, row_stride, (float *)workspace);
     IPR_LAUNCH_CHECK();
-    IPR_LAUNCH_PDL((colsum_stage2), (ncols + 255) / 256, 256, 0, ipr_cu(stream), (const float *)workspace, G, ncols, out, accumulate, scale,
+    IPR_LAUNCH_PDL((colsum_stage2), (ncols + 31) / 32, 256, 0, ipr_cu(stream), (const float *)workspace, G, ncols, out, accumulate, scale,
                    (const int *)nullptr);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
@@ -635,7 +653,7 @@ extern "C" int ipr_colsum_bf16(const void *x, int64_t rows, int channels, float 
     const int threads = c_vec < 256 ? ((c_vec + 31) / 32) * 32 : 256;
     IPR_LAUNCH_PDL((colsum_bf16_stage1), grid, threads, 0, ipr_cu(stream), (const uint4 *)x, rows, c_vec, (float *)workspace);
     IPR_LAUNCH_CHECK();
-    IPR_LAUNCH_PDL((colsum_stage2), (channels + 255) / 256, 256, 0, ipr_cu(stream), (const float *)workspace, G, channels, out,
+    IPR_LAUNCH_PDL((colsum_stage2), (channels + 31) / 32, 256, 0, ipr_cu(stream), (const float *)workspace, G, channels, out,
                    accumulate, scale, out_index);
     IPR_LAUNCH_CHECK();
     return IPR_OK;

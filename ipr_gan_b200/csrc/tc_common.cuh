@@ -37,10 +37,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
-// Long waits (epilogue warps waiting for a whole main loop): back off between probes so that 128 spinning threads do
-// not compete with the single TMA-producer / MMA-issuer threads for issue slots and the mbarrier unit.
+// Long waits (epilogue warps waiting for a whole main loop).  mbarrier.try_wait is itself a suspending wait with a
+// hardware time limit, so the first probes cost no issue slots; only a wait that outlives many of them backs off with a
+// short sleep.  (The first version slept 256 ns after every failed probe: with 1-2 us tiles -- the single-k-block patch
+// GEMMs run 27 tiles per CTA in 49 us -- the sleep quantum itself throttled the accumulator hand-over; ncu,
+// profiles/r2_linear_case_full.txt: tensor pipe 5 %, DRAM 12 %, issue slots 35 % busy.)
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
+    int probes = 0;
     while (true) {
         asm volatile(
             "{\n\t"
@@ -49,7 +53,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(256);
+        if (++probes > 64) __nanosleep(64);
     }
 }
 
