@@ -60,8 +60,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-template <int BLOCK_N, int STAGES, int MT, bool RES, int EPI_WARPS>
-__global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1)
+// OCC = 2: two CTAs per SM for layers whose tiles have a short main loop (few k-blocks): there the epilogue -- one
+// warp per 32 rows walking its columns at ~0.2 instructions per cycle, ~2000 cycles per 128 x 64 tile (per-tile
+// timestamps, scripts/tile_phase_probe3.py) -- is the pace maker, and a second CTA doubles the epilogue warps per SM.
+// To fit, the variant keeps 3 smem stages, drains the accumulator 16 columns at a time (half the live registers:
+// <= 102 per thread) and stores rows directly.
+template <int BLOCK_N, int STAGES, int MT, bool RES, int EPI_WARPS, int OCC = 1>
+__global__ void __launch_bounds__(64 + EPI_WARPS * 32, OCC)
 tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                const __grid_constant__ CUtensorMap mapB, const TgParams p)
@@ -75,7 +80,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     constexpr uint32_t BUF_COLS = MT * ACC_COLS;
     constexpr uint32_t TMEM_COLS = 2 * BUF_COLS;                     // double-buffered: epilogue(i) overlaps mainloop(i+1)
     static_assert(TMEM_COLS <= 512, "TMEM budget");
-    constexpr int CH = BLOCK_N >= 32 ? 32 : 16;                      // columns per tcgen05.ld
+    constexpr int CH = (BLOCK_N >= 32 && OCC == 1) ? 32 : 16;        // columns per tcgen05.ld
     constexpr int N_CHUNKS = BLOCK_N / CH;
     constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
     constexpr int EPI_GROUPS = EPI_WARPS / 4;                        // warps per TMEM lane quarter
@@ -100,6 +105,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
     // per-warp running column statistics [epilogue warp][sum | sumsq][CH_PER_WARP * CH] floats (after the mbarriers)
     float *stat_sm = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * A_BYTES + b_region + 256);
+    // per-epilogue-warp staging (2 KB each) for the transposed bf16 store: behind the statistics slots, 16-byte aligned
+    uint8_t *stage_sm = reinterpret_cast<uint8_t *>(stat_sm) + 8 * BLOCK_N * 4;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.dbg && threadIdx.x == 0) {
@@ -398,8 +405,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
 
-                if (!valid) continue;
                 if (p.epi_mode == IPR_EPI_TANH_NCHW || p.epi_mode == IPR_EPI_LINEAR_NCHW) {
+                    if (!valid) continue;
                     const size_t hw = (size_t)p.out_h * p.out_w, img = pix / hw, inner = pix - img * hw;
                     float *o = reinterpret_cast<float *>(p.out) + img * p.out_c * hw + inner;
 #pragma unroll
@@ -408,6 +415,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         if (n < p.n_valid) o[(size_t)n * hw] = v[j];
                     }
                 } else if (p.epi_mode == IPR_EPI_LINEAR_F32) {
+                    if (!valid) continue;
                     float *o = reinterpret_cast<float *>(p.out) + pix * p.out_c + n0;
                     if (n0 + CH <= p.n_valid && (p.out_c & 3) == 0) {
 #pragma unroll
@@ -419,15 +427,41 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 } else {
                     __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.out_c + n0;
-                    if (n0 + CH <= p.n_valid) {
+                    if (n0 + CH <= p.n_valid) {            // (warp-uniform)
+                        uint4 pk[CH / 8];
 #pragma unroll
                         for (int gq = 0; gq < CH / 8; gq++) {
-                            uint4 pk;
-                            pk.x = pack_bf16x2(v[gq * 8 + 0], v[gq * 8 + 1]); pk.y = pack_bf16x2(v[gq * 8 + 2], v[gq * 8 + 3]);
-                            pk.z = pack_bf16x2(v[gq * 8 + 4], v[gq * 8 + 5]); pk.w = pack_bf16x2(v[gq * 8 + 6], v[gq * 8 + 7]);
-                            reinterpret_cast<uint4 *>(o)[gq] = pk;
+                            pk[gq].x = pack_bf16x2(v[gq * 8 + 0], v[gq * 8 + 1]); pk[gq].y = pack_bf16x2(v[gq * 8 + 2], v[gq * 8 + 3]);
+                            pk[gq].z = pack_bf16x2(v[gq * 8 + 4], v[gq * 8 + 5]); pk[gq].w = pack_bf16x2(v[gq * 8 + 6], v[gq * 8 + 7]);
                         }
-                    } else {
+                        if constexpr (CH == 32) {
+                            // Every thread owns one output row (64 bytes of it per chunk).  Storing it as four 16-byte
+                            // pieces makes each store instruction touch 32 different lines -- the LSU needs ~32 cycles
+                            // per instruction, which paced the small-K layers (ncu, profiles/r2_linear_case_full.txt:
+                            // tensor pipe 5 %, epilogue warps waiting).  Transposed through a 2 KB per-warp staging
+                            // area (XOR-swizzled 16-byte slots: conflict-free both ways) one instruction writes 8 rows
+                            // x 64 contiguous bytes: a quarter of the line touches.
+                            uint8_t *stg = stage_sm + warp * 2048;
+#pragma unroll
+                            for (int gq = 0; gq < 4; gq++)
+                                *reinterpret_cast<uint4 *>(stg + lane * 64 + ((gq ^ ((lane >> 1) & 3)) << 4)) = pk[gq];
+                            __syncwarp();
+                            const unsigned long long optr = valid ? reinterpret_cast<unsigned long long>(o) : 0ull;
+#pragma unroll
+                            for (int jj = 0; jj < 4; jj++) {
+                                const int R = 8 * jj + (lane >> 2), pz = lane & 3;
+                                const uint4 val = *reinterpret_cast<const uint4 *>(stg + R * 64 + ((pz ^ ((R >> 1) & 3)) << 4));
+                                const unsigned long long rp = __shfl_sync(0xffffffffu, optr, R);
+                                if (rp) *reinterpret_cast<uint4 *>(rp + pz * 16) = val;
+                            }
+                            __syncwarp();
+                        } else {
+                            if (valid) {
+#pragma unroll
+                                for (int gq = 0; gq < CH / 8; gq++) reinterpret_cast<uint4 *>(o)[gq] = pk[gq];
+                            }
+                        }
+                    } else if (valid) {
 #pragma unroll
                         for (int j = 0; j < CH; j++) if (n0 + j < p.n_valid) o[j] = __float2bfloat16(v[j]);
                     }
@@ -454,25 +488,38 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
 }
 
-template <int BLOCK_N, int STAGES, int MT, bool RES, int EW>
+template <int BLOCK_N, int STAGES, int MT, bool RES, int EW, int OCC = 1>
 int launch_ew(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3 grid, cudaStream_t st)
 {
     const size_t b_region = RES ? (size_t)p.n_phases * p.n_taps * p.c_chunks * BLOCK_N * BLOCK_K * 2
                                 : (size_t)STAGES * BLOCK_N * BLOCK_K * 2;
-    const size_t smem = (size_t)STAGES * MT * A_STAGE_BYTES + b_region + 256 + 8 * BLOCK_N * 4 + 1024 + 64;
-    if (smem > 227 * 1024) return IPR_E_UNSUPPORTED;
+    const size_t smem = (size_t)STAGES * MT * A_STAGE_BYTES + b_region + 256 + 8 * BLOCK_N * 4 + (OCC == 1 ? 8 * 2048 : 0) + 1024 + 64;
+    if (smem > (size_t)(OCC == 1 ? 227 : 113) * 1024) return IPR_E_UNSUPPORTED;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (OCC == 1 ? 227 : 113) * 1024);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
     const int total = (int)(((grid.x + MT - 1) / MT) * grid.y * grid.z);
-    const int ctas = total < ipr_sm_count() ? total : ipr_sm_count();       // persistent: one CTA per SM
-    IPR_LAUNCH_PDL((tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW>), ctas, 64 + EW * 32, smem, st, ma[0], ma[1], ma[2], ma[3], mb, p);
+    const int slots = ipr_sm_count() * OCC;                                  // persistent: OCC CTAs per SM
+    const int ctas = total < slots ? total : slots;
+    IPR_LAUNCH_PDL((tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC>), ctas, 64 + EW * 32, smem, st, ma[0], ma[1], ma[2], ma[3], mb, p);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
+}
+
+// Two CTAs per SM pay off where a tile's main loop is shorter than its epilogue: few k-blocks per tile, enough tiles.
+bool use_two_ctas(const ipr_tapgemm_t *d, const TgParams &p)
+{
+    static const char *off = getenv("IPR_TG_NO_OCC2");
+    if (off) return false;
+    const int num_kb = d->n_taps * ((d->a_c + BLOCK_K - 1) / BLOCK_K);
+    const long long tiles = (long long)p.m_tiles * (d->n_total / d->block_n) * d->n_phases;
+    const int kb_limit = d->block_n == 64 ? 10 : 5;                          // main loop <= ~1300 cycles
+    return (d->block_n == 64 || d->block_n == 128) && num_kb <= kb_limit && tiles >= 4LL * ipr_sm_count() &&
+           d->epi_mode != IPR_EPI_TANH_NCHW && d->epi_mode != IPR_EPI_LINEAR_NCHW;
 }
 
 template <int BLOCK_N, int STAGES, int MT, bool RES>
@@ -516,7 +563,8 @@ extern "C" int ipr_tapgemm_stats_rows(const ipr_tapgemm_t *d)
     if (rc != IPR_OK) return rc;
     IPR_REQUIRE(d->block_n > 0 && d->n_total % d->block_n == 0 && d->n_phases >= 1, IPR_E_SHAPE);
     const long long tiles = (long long)p.m_tiles * d->n_phases;
-    if (d->n_total == d->block_n) return (int)(4 * (tiles < ipr_sm_count() ? tiles : ipr_sm_count()));
+    const long long slots = (long long)ipr_sm_count() * (use_two_ctas(d, p) ? 2 : 1);
+    if (d->n_total == d->block_n) return (int)(4 * (tiles < slots ? tiles : slots));
     return (int)(4 * tiles);
 }
 
@@ -608,8 +656,14 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     // weights resident in shared memory: one N block, everything (all phases x taps) fits beside 4 A stages, and every
     // CTA has at least two tiles to amortise the one-off weight load over
     const size_t b_all = (size_t)d->n_phases * d->n_taps * p.c_chunks * d->block_n * BLOCK_K * 2;
-    const bool resident = d->n_total == d->block_n && b_all <= 150 * 1024 && single_tiles >= 2LL * ipr_sm_count() &&
+    const bool resident = d->n_total == d->block_n && b_all <= 132 * 1024 && single_tiles >= 2LL * ipr_sm_count() &&
                           getenv("IPR_TG_NO_RESIDENT") == nullptr;
+    if (!pair && use_two_ctas(d, p)) {
+        const bool heavy = p.epi_mode == IPR_EPI_BIAS_LRELU || p.epi_mode == IPR_EPI_MASK || p.stats != nullptr;
+        (void)heavy;
+        if (d->block_n == 64) return launch_ew<64, 3, 1, false, 8, 2>(ma, mb, p, grid, st);
+        return launch_ew<128, 3, 1, false, 8, 2>(ma, mb, p, grid, st);
+    }
     if (resident) {
         switch (d->block_n) {
             case 16:  return launch<16, 4, 1, true>(ma, mb, p, grid, st);

@@ -173,7 +173,7 @@ class Plan(object):
             if self.n_total % bn == 0:
                 tiles = m_tiles * (self.n_total // bn) * self.n_phases
                 b_all = self.n_phases * self.n_taps * C * bn * 2
-                resident = bn == self.n_total and b_all <= 150 * 1024 and tiles >= 2 * _SM_COUNT   # weights stay in smem
+                resident = bn == self.n_total and b_all <= 132 * 1024 and tiles >= 2 * _SM_COUNT   # weights stay in smem
                 cost = -(-tiles // _SM_COUNT) * (128 + (0 if resident else bn)) * (1.0 if bn >= 64 else 1.5)
                 if best is None or cost < best:
                     best, block_n = cost, bn
