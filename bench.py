@@ -473,77 +473,72 @@ def run_verify(args):
     _finish(world)
 
 
-def run_family(args):
-    """BASELINE configs 3 / 4: one protected training step of IPR-SRGAN (experiments/image_super_resolution.py:84-113) or
-    IPR-CycleGAN (experiments/image_translation.py:90-112) through the drop-in models, networks on the native engine."""
+def build_family(workload, use_graph=True):
+    """-> (trainer, workload name, pinned host inputs) of BASELINE config 3 (srgan) / 4 (cyclegan)."""
     import torch
-    import ipr_gan_b200
-    ipr_gan_b200.enable_dropin()
-    import models
-    from configs import Config
-    from configs.presets import WATERMARK_A
-    from ipr_gan_b200 import _lib
-    os.environ.setdefault("IPR_VGG_RANDOM_INIT", "1")          # no network: seeded random VGG weights (outside the path)
+    from ipr_gan_b200 import trainer as T
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    torch.manual_seed(1234)
     gen = torch.Generator().manual_seed(1234)
-    if args.workload == "srgan":
-        m = models.SRGAN(Config({"G": "SRResNet", "D": "Discriminator96", "V": "VGG19Feature", "opt": "Adam",
-                                 "opt_param": {"lr": 1.0e-4, "betas": [0.9, 0.999]}, "type": "SRGAN"}), device=[dev])
-        m = models.BlackBoxWrapper(m, Config({"fn_inp": {"type": "RandomNoisePatch", "size": 12},
-                                              "fn_out": {"size": 48, "opaque": True, "type": "PasteWatermark", "watermark": WATERMARK_A},
-                                              "lambda": 1.0, "loss_fn": "ssim", "normalized": False, "input_var": "low_res",
-                                              "output_var": "super_res", "target": "G"}))
-        m = models.WhiteBoxWrapper(m, Config({"gamma_0": 0.1, "string": "EXAMPLE A", "target": "G"}))
-        lr_h, hr_h = torch.rand(16, 3, 24, 24, generator=gen).pin_memory(), torch.rand(16, 3, 96, 96, generator=gen).pin_memory()
-
-        def step():
-            m.update_g({"low_res": lr_h.to(dev, non_blocking=True), "high_res": hr_h.to(dev, non_blocking=True), "pretrain": False})
-            m.update_d({"high_res": m.high_res, "super_res": m.super_res})
-            return m.get_metrics()
-        name, h2d = "IPR-SRGAN 24->96 protected step, batch 16 (SRResNet + Discriminator96 + VGG content loss)", (lr_h.numel() + hr_h.numel()) * 4
+    if workload == "srgan":
+        tr = T.ProtectedSRGANTrainer(16, dev, use_graph=use_graph)
+        host = (torch.rand(16, 3, 24, 24, generator=gen).pin_memory(), torch.rand(16, 3, 96, 96, generator=gen).pin_memory())
+        name = "IPR-SRGAN 24->96 protected step, batch 16 (SRResNet + Discriminator96 + VGG content loss)"
     else:
-        m = models.CycleGAN(Config({"G": "Resnet9Blocks", "D": "ConvDiscriminator", "lambda_A": 10.0, "lambda_B": 10.0,
-                                    "lambda_idt": 0.5, "opt": "Adam", "opt_param": {"lr": 2.0e-4, "betas": [0.5, 0.999]},
-                                    "pool_size": 50, "epoch": 200, "type": "CycleGAN"}), device=[dev])
-        m = models.BlackBoxWrapper(m, Config({"fn_inp": {"type": "RandomNoisePatch", "size": 64},
-                                              "fn_out": {"size": 64, "opaque": True, "type": "PasteWatermark", "watermark": WATERMARK_A},
-                                              "lambda": 1.0, "loss_fn": "ssim", "normalized": True, "input_var": "real_B",
-                                              "output_var": "fake_A", "target": "GB"}))
-        m = models.WhiteBoxWrapper(m, Config({"gamma_0": 0.1, "string": "EXAMPLE A", "target": "GB"}))
-        a_h = (torch.rand(1, 3, 128, 128, generator=gen) * 2 - 1).pin_memory()
-        b_h = (torch.rand(1, 3, 128, 128, generator=gen) * 2 - 1).pin_memory()
+        tr = T.ProtectedCycleGANTrainer(dev, 128, use_graph=use_graph)
+        host = ((torch.rand(1, 3, 128, 128, generator=gen) * 2 - 1).pin_memory(),
+                (torch.rand(1, 3, 128, 128, generator=gen) * 2 - 1).pin_memory())
+        name = "IPR-CycleGAN 128x128 protected step, batch 1 (Resnet9Blocks x2 + PatchGAN x2, InstanceNorm sign loss)"
+    for dst, src in zip((tr.low_res, tr.high_res) if workload == "srgan" else (tr.real_A, tr.real_B), host):
+        dst.copy_(src)
+    return tr, name, host
 
-        def step():
-            m.update_g({"real_A": a_h.to(dev, non_blocking=True), "real_B": b_h.to(dev, non_blocking=True)})
-            m.update_d({"real_A": m.real_A, "real_B": m.real_B, "fake_A": m.fake_A.detach(), "fake_B": m.fake_B.detach()})
-            return m.get_metrics()
-        name, h2d = "IPR-CycleGAN 128x128 protected step, batch 1 (Resnet9Blocks x2 + PatchGAN x2, InstanceNorm sign loss)", (a_h.numel() + b_h.numel()) * 4
+
+def run_family(args):
+    """BASELINE configs 3 / 4: one protected training step of IPR-SRGAN (experiments/image_super_resolution.py:84-113) or
+    IPR-CycleGAN (experiments/image_translation.py:90-112) through the drop-in models, networks on the native engine;
+    the step replays as CUDA graph(s) (ipr_gan_b200/trainer.py), host batch in / metrics out inside the timed region."""
+    import torch
+    from ipr_gan_b200 import _lib
+    tr, name, host = build_family(args.workload, use_graph=not args.no_graph)
+    dev = tr.device
+    tr.capture(max(3, args.warmup))
     for _ in range(max(3, args.warmup)):
-        last = step()
+        last = tr.step_from_host(*host)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     sampler = ClockSampler(0)
     sampler.start()
     torch.cuda.synchronize()
-    total, before = 0.0, _lib.launch_count()
+    total, dev_total = 0.0, 0.0
     for _ in range(args.steps):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        last = step()
+        last = tr.step_from_host(*host)
         b.record()
         torch.cuda.synchronize()
         total += a.elapsed_time(b)
-    launches = _lib.launch_count() - before
+    # device-resident variant: inputs already in HBM, no read-back inside the timed region
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        tr.step()
+    b.record()
+    torch.cuda.synchronize()
+    dev_ms = a.elapsed_time(b) / args.steps
+    launches = (tr.launches_per_step or 0) * args.steps
     ms = total / args.steps
-    print(json.dumps({"metric": name + ", steps/sec", "value": 1e3 / ms, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
-                      "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    h2d = sum(t.numel() * 4 for t in host)
+    print(json.dumps({"metric": name + ", steps/sec", "value": 1e3 / dev_ms, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(3, args.warmup), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                      "config": {"workload": name, "l2": "flushed between steps", "timing": "CUDA events around each eager step, host "
-                                 "batch in / metrics out inside the timed region (so value == e2e)"},
+                      "config": {"workload": name, "cuda_graph": tr.use_graph, "l2": "e2e: flushed between steps; value: back-to-back "
+                                 "replays (activations of one step exceed L2)",
+                                 "timing": "CUDA events; value = inputs resident, e2e = pinned host batch in / metrics out per step"},
                       "clocks": sampler.stop(), "gpu_launches": int(launches),
-                      "e2e": {"value": 1e3 / ms, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 64},
+                      "e2e": {"value": 1e3 / ms, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 64,
+                              "ms_per_step": ms},
                       "last_metrics": last}))
 
 

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libipr_b200.so")
+LIB_PATH = os.environ.get("IPR_B200_LIB") or os.path.join(_PKG, "libipr_b200.so")   # override: A/B runs of two builds
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

@@ -53,6 +53,7 @@ struct TgParams {
     int n_valid;
     float *stats;
     long long *dbg;        // optional phase timestamps of CTA 0 (scripts/tile_phase_probe.py)
+    int dbg_flags;         // probes only (IPR_TG_DBG_FLAGS): 1 = skip the output stores, 2 = skip the bias / activation math
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -305,7 +306,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int sub = 0; sub < MT; sub++) {
             const int m_tile = m_grp * MT + sub;
             const long long pix_s = row_pix(ct, sub);
-            const bool valid = pix_s >= 0;
+            const bool valid = pix_s >= 0 && !(p.dbg_flags & 1);
             const size_t pix = (size_t)pix_s;
 #pragma unroll 1
             for (int c0 = c_begin; c0 < c_end; c0 += CH) {
@@ -331,7 +332,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < CH; j++) v[j] = __uint_as_float(raw[j]) * inv_sigma;
 
-                if (p.epi_mode == IPR_EPI_BIAS_LRELU) {
+                if (p.epi_mode == IPR_EPI_BIAS_LRELU && !(p.dbg_flags & 2)) {
                     if (bias_vec) {                        // 8 broadcast 128-bit loads instead of 32 scalar ones
 #pragma unroll
                         for (int j4 = 0; j4 < CH / 4; j4++) {
@@ -513,8 +514,10 @@ int launch_ew(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, d
 // Two CTAs per SM pay off where a tile's main loop is shorter than its epilogue: few k-blocks per tile, enough tiles.
 bool use_two_ctas(const ipr_tapgemm_t *d, const TgParams &p)
 {
-    static const char *off = getenv("IPR_TG_NO_OCC2");
-    if (off) return false;
+    // Measured on B200 (scripts/ab_run.sh, batch 512): the variant LOSES -- patch GEMM 32->64 47 -> 69 us, conv4s2_dgrad
+    // 64->64 78 -> 112 us, step 4.05 -> 4.39 ms -- so it is opt-in (IPR_TG_OCC2=1) and kept only as a probe.
+    static const char *on = getenv("IPR_TG_OCC2");
+    if (!on) return false;
     const int num_kb = d->n_taps * ((d->a_c + BLOCK_K - 1) / BLOCK_K);
     const long long tiles = (long long)p.m_tiles * (d->n_total / d->block_n) * d->n_phases;
     const int kb_limit = d->block_n == 64 ? 10 : 5;                          // main loop <= ~1300 cycles
@@ -615,6 +618,7 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     p.out_h = d->out_h; p.out_w = d->out_w; p.out_c = d->out_c; p.out_sh = d->out_sh; p.out_sw = d->out_sw;
     p.n_valid = d->n_valid > 0 ? d->n_valid : d->n_total; p.stats = d->stats;
     { const char *e = getenv("IPR_TG_DBG_PTR"); p.dbg = e ? (long long *)strtoull(e, nullptr, 0) : nullptr; }
+    { const char *e = getenv("IPR_TG_DBG_FLAGS"); p.dbg_flags = e ? atoi(e) : 0; }
 
     // ---- tensor maps (host-encoded, passed by value as kernel parameters: graph-capturable)
     CUtensorMap ma[4], mb;

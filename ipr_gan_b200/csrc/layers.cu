@@ -291,8 +291,12 @@ norm_stats_kernel(const uint4 *__restrict__ x, float *__restrict__ partial, long
     }
 }
 
-// scale / shift / mean / rstd per (group, channel) from the slab partials; BatchNorm running statistics (groups == 1)
-__global__ void __launch_bounds__(256)
+// scale / shift / mean / rstd per (group, channel) from the slab partials; BatchNorm running statistics (groups == 1).
+// CTA = 32 (group, channel) columns x FIN_LANES slab lanes: every thread adds every FIN_LANES-th slab (double, fixed
+// order), the lanes are combined in order through shared memory.  (The first version walked all <= 256 slabs with one
+// thread per column: 47 us of serial load latency per launch, 87 launches in one SRGAN step.)
+constexpr int FIN_LANES = 16;
+__global__ void __launch_bounds__(32 * FIN_LANES)
 norm_finalize_kernel(const float *__restrict__ partial, int groups, int slabs, int C, double count, float eps, float momentum,
                      const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ running_mean,
                      float *__restrict__ running_var, long long *__restrict__ num_batches, float *__restrict__ scale,
@@ -300,15 +304,23 @@ norm_finalize_kernel(const float *__restrict__ partial, int groups, int slabs, i
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && num_batches) *num_batches += 1;
-    if (i >= groups * C) return;
-    const int g = i / C, c = i - g * C;
+    __shared__ double sm[2][FIN_LANES][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches) *num_batches += 1;
+    const bool live = i < groups * C;
+    const int g = live ? i / C : 0, c = live ? i - g * C : 0;
     double a = 0.0, b = 0.0;
-    for (int s = 0; s < slabs; s++) {
-        a += (double)partial[((size_t)(g * slabs + s) * 2) * C + c];
-        b += (double)partial[((size_t)(g * slabs + s) * 2 + 1) * C + c];
-    }
+    if (live)
+        for (int s = ty; s < slabs; s += FIN_LANES) {
+            a += (double)partial[((size_t)(g * slabs + s) * 2) * C + c];
+            b += (double)partial[((size_t)(g * slabs + s) * 2 + 1) * C + c];
+        }
+    sm[0][ty][tx] = a; sm[1][ty][tx] = b;
+    __syncthreads();
+    if (ty != 0 || !live) return;
+#pragma unroll
+    for (int y = 1; y < FIN_LANES; y++) { a += sm[0][y][tx]; b += sm[1][y][tx]; }
     const double mean = a / count;
     double var = b / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -412,52 +424,68 @@ norm_bwd_reduce_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x
     }
 }
 
-// backward pass 2 (one CTA): per (group, channel) coefficients  dx = A*gin + B*x + D;  dgamma / dbeta summed over the
-// groups (+ the sign-loss gradient); PReLU slope gradient summed over everything.
-__global__ void __launch_bounds__(256)
+// backward pass 2: per (group, channel) coefficients  dx = A*gin + B*x + D;  dgamma / dbeta summed over the groups
+// (+ the sign-loss gradient); PReLU slope gradient summed over everything.
+// CTAs 0 .. ceil(C/32)-1 (has_norm): 32 channels x FIN_LANES slab lanes each, groups walked in order; the LAST CTA (dslope)
+// adds up the slope-gradient plane in a fixed order.  (The first version was ONE CTA with one thread per channel walking
+// groups x slabs rows serially: 103 us per launch, a quarter of the SRGAN step.)
+__global__ void __launch_bounds__(32 * FIN_LANES)
 norm_bwd_finalize_kernel(const float *__restrict__ partial, int groups, int slabs, int C, double count,
                          const float *__restrict__ gamma, const float *__restrict__ mean, const float *__restrict__ rstd,
                          float *__restrict__ dgamma, float *__restrict__ dbeta, int accumulate,
                          const float *__restrict__ sign, float gamma0, float sign_scale, float *__restrict__ dslope,
-                         int has_norm, float *__restrict__ coef)
+                         int has_norm, float *__restrict__ coef, int norm_ctas)
 {
     ipr_pdl_wait();
     ipr_pdl_trigger();
+    __shared__ double sm[2][FIN_LANES][33];
     __shared__ float red[32];
-    float pre_sum = 0.0f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double dg = 0.0, db = 0.0;
-        for (int g = 0; g < groups; g++) {
-            double sg = 0.0, sx = 0.0, sp = 0.0;
-            for (int s = 0; s < slabs; s++) {
+    if ((int)blockIdx.x >= norm_ctas) {              // the slope-gradient CTA
+        double acc = 0.0;
+        const long long total = (long long)groups * slabs * C;
+        for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+            const long long row = e / C;
+            acc += (double)partial[(size_t)row * 3 * C + 2 * C + (int)(e - row * C)];
+        }
+        const float tot = ipr_block_sum((float)acc, red);
+        if (threadIdx.x == 0) *dslope = accumulate ? *dslope + tot : tot;
+        return;
+    }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const bool live = c < C;
+    double dg = 0.0, db = 0.0;
+    for (int g = 0; g < groups; g++) {
+        double sg = 0.0, sx = 0.0;
+        if (live)
+            for (int s = ty; s < slabs; s += FIN_LANES) {
                 const float *row = partial + (size_t)(g * slabs + s) * 3 * C;
-                sg += (double)row[c]; sx += (double)row[C + c]; sp += (double)row[2 * C + c];
+                sg += (double)row[c]; sx += (double)row[C + c];
             }
-            pre_sum += (float)sp;
-            if (has_norm) {
-                const int ci = g * C + c;
-                const float ga = gamma ? gamma[c] : 1.0f, rs = rstd[ci], mu = mean[ci];
-                const float A = ga * rs;
-                const float B = -ga * rs * rs * (float)(sx / count);
-                coef[ci] = A;
-                coef[groups * C + ci] = B;
-                coef[2 * groups * C + ci] = -A * (float)(sg / count) - B * mu;
-            }
+        __syncthreads();                             // previous group's lanes have been read
+        sm[0][ty][tx] = sg; sm[1][ty][tx] = sx;
+        __syncthreads();
+        if (ty == 0 && live) {
+#pragma unroll
+            for (int y = 1; y < FIN_LANES; y++) { sg += sm[0][y][tx]; sx += sm[1][y][tx]; }
+            const int ci = g * C + c;
+            const float ga = gamma ? gamma[c] : 1.0f, rs = rstd[ci], mu = mean[ci];
+            const float A = ga * rs;
+            const float B = -ga * rs * rs * (float)(sx / count);
+            coef[ci] = A;
+            coef[groups * C + ci] = B;
+            coef[2 * groups * C + ci] = -A * (float)(sg / count) - B * mu;
             dg += sx; db += sg;
         }
-        if (has_norm && dgamma) {
-            float dgf = (float)dg;
-            if (sign) {                              // d/dgamma of mean_c relu(gamma0 - gamma*sign)
-                const float sv = sign[c];
-                if (gamma0 - gamma[c] * sv > 0.0f) dgf += -sv * sign_scale / (float)C;
-            }
-            dgamma[c] = accumulate ? dgamma[c] + dgf : dgf;
-            dbeta[c] = accumulate ? dbeta[c] + (float)db : (float)db;
-        }
     }
-    if (dslope) {
-        const float tot = ipr_block_sum(pre_sum, red);
-        if (threadIdx.x == 0) *dslope = accumulate ? *dslope + tot : tot;
+    if (ty == 0 && live && dgamma) {
+        float dgf = (float)dg;
+        if (sign) {                                  // d/dgamma of mean_c relu(gamma0 - gamma*sign)
+            const float sv = sign[c];
+            if (gamma0 - gamma[c] * sv > 0.0f) dgf += -sv * sign_scale / (float)C;
+        }
+        dgamma[c] = accumulate ? dgamma[c] + dgf : dgf;
+        dbeta[c] = accumulate ? dbeta[c] + (float)db : (float)db;
     }
 }
 
@@ -617,7 +645,7 @@ extern "C" int ipr_norm_fwd_bf16(const void *x, void *y, const void *residual, i
         float *partial = (float *)workspace;
         IPR_LAUNCH_PDL((norm_stats_kernel), groups * slabs, threads, smem, st, (const uint4 *)x, partial, (long long)rows, c_vec, slabs);
         IPR_LAUNCH_CHECK();
-        IPR_LAUNCH_PDL((norm_finalize_kernel), (groups * channels + 255) / 256, 256, 0, st, partial, groups, slabs, channels,
+        IPR_LAUNCH_PDL((norm_finalize_kernel), (groups * channels + 31) / 32, 32 * FIN_LANES, 0, st, partial, groups, slabs, channels,
                        (double)rows, eps, momentum, gamma, beta, running_mean, running_var, (long long *)num_batches_tracked,
                        scale, shift, mean, rstd);
         IPR_LAUNCH_CHECK();
@@ -666,8 +694,11 @@ extern "C" int ipr_norm_bwd_bf16(const void *dy, const void *x, void *dx, int gr
                        has_norm ? scale : (const float *)nullptr, shift, mean, rstd, partial, (long long)rows, c_vec, slabs, act,
                        slope, slope_ptr);
         IPR_LAUNCH_CHECK();
-        IPR_LAUNCH_PDL((norm_bwd_finalize_kernel), 1, 256, 0, st, (const float *)partial, groups, slabs, channels, (double)rows,
-                       gamma, mean, rstd, dgamma, dbeta, accumulate, sign, gamma0, sign_scale, dslope, has_norm, coef);
+        const int norm_ctas = has_norm ? (channels + 31) / 32 : 0;
+        const bool slope_cta = dslope != nullptr;
+        IPR_LAUNCH_PDL((norm_bwd_finalize_kernel), norm_ctas + (slope_cta ? 1 : 0), 32 * FIN_LANES, 0, st, (const float *)partial,
+                       groups, slabs, channels, (double)rows, gamma, mean, rstd, dgamma, dbeta, accumulate, sign, gamma0,
+                       sign_scale, dslope, has_norm, coef, norm_ctas);
         IPR_LAUNCH_CHECK();
     }
     IPR_LAUNCH_PDL((norm_bwd_apply_kernel), grid_1d(n_vec, 256), 256, 0, st, (const uint4 *)dy, (const uint4 *)x,

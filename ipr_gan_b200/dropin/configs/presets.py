@@ -26,3 +26,34 @@ def dcgan_blackbox(fn_inp="TransformDist", wm_size=16, opaque=True, lam=1.0, wat
 
 def dcgan_whitebox(gamma_0=0.1, string="EXAMPLE A"):
     return Config({"gamma_0": gamma_0, "string": string, "target": "G"})
+
+
+# ---- BASELINE config 3: IPR-SRGAN 24 -> 96 (configs/SRGAN/complete/*.yaml: noise-patch trigger, pasted watermark, SSIM)
+def srgan_model():
+    return Config({"G": "SRResNet", "D": "Discriminator96", "V": "VGG19Feature", "opt": "Adam",
+                   "opt_param": {"lr": 1.0e-4, "betas": [0.9, 0.999]}, "type": "SRGAN"})
+
+
+def srgan_blackbox(watermark=WATERMARK_A):
+    return Config({"fn_inp": {"type": "RandomNoisePatch", "size": 12},
+                   "fn_out": {"size": 48, "opaque": True, "type": "PasteWatermark", "watermark": watermark},
+                   "lambda": 1.0, "loss_fn": "ssim", "normalized": False, "input_var": "low_res",
+                   "output_var": "super_res", "target": "G"})
+
+
+# ---- BASELINE config 4: IPR-CycleGAN (configs/CycleGAN/complete/*.yaml: protects GB, InstanceNorm sign loss)
+def cyclegan_model():
+    return Config({"G": "Resnet9Blocks", "D": "ConvDiscriminator", "lambda_A": 10.0, "lambda_B": 10.0,
+                   "lambda_idt": 0.5, "opt": "Adam", "opt_param": {"lr": 2.0e-4, "betas": [0.5, 0.999]},
+                   "pool_size": 50, "epoch": 200, "type": "CycleGAN"})
+
+
+def cyclegan_blackbox(watermark=WATERMARK_A):
+    return Config({"fn_inp": {"type": "RandomNoisePatch", "size": 64},
+                   "fn_out": {"size": 64, "opaque": True, "type": "PasteWatermark", "watermark": watermark},
+                   "lambda": 1.0, "loss_fn": "ssim", "normalized": True, "input_var": "real_B",
+                   "output_var": "fake_A", "target": "GB"})
+
+
+def whitebox(target, gamma_0=0.1, string="EXAMPLE A"):
+    return Config({"gamma_0": gamma_0, "string": string, "target": target})

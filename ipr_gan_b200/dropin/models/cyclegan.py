@@ -132,7 +132,10 @@ class CycleGAN(Model):
     # ---- discriminator step (models/cyclegan.py:107-120, 145-164)
     def forward_d(self, data):
         self.real_A, self.real_B = data["real_A"], data["real_B"]
-        self.fake_A, self.fake_B = self.poolA(data["fake_A"]), self.poolB(data["fake_B"])
+        if data.get("pooled", False):      # the caller already exchanged the images with the history pools
+            self.fake_A, self.fake_B = data["fake_A"], data["fake_B"]      # (trainer.ProtectedCycleGANTrainer)
+        else:
+            self.fake_A, self.fake_B = self.poolA(data["fake_A"]), self.poolB(data["fake_B"])
         self.RA_logits, self.FA_logits = self.DB(self.real_A), self.DB(self.fake_A.detach())
         self.RB_logits, self.FB_logits = self.DA(self.real_B), self.DA(self.fake_B.detach())
 

@@ -95,3 +95,149 @@ class ProtectedDCGANTrainer(object):
         self.set_inputs(real_cpu, latent_cpu)
         self.step()
         return self.model.get_metrics()
+
+
+# ------------------------------------------------------------------------------------------ SRGAN / CycleGAN
+def _capture(fn, device, warmup=3, stream=None):
+    """Warm ``fn`` up eagerly on a side stream, then capture it into a CUDA graph (weight packing included).
+    Warm-up and capture use the SAME stream: autograd's AccumulateGrad nodes remember the stream they were created
+    on, and a node from an uncaptured stream inside a capture is a capture-isolation error.
+    -> (graph, library launches inside the captured region)"""
+    s = stream if stream is not None else torch.cuda.Stream(device=device)
+    s.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(s):
+        for _ in range(warmup):
+            fn()
+    torch.cuda.current_stream(device).wait_stream(s)
+    torch.cuda.synchronize(device)
+    engine.reset_caches()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s, capture_error_mode="thread_local"):
+        before = _lib.launch_count()
+        fn()
+        launches = _lib.launch_count() - before
+    torch.cuda.synchronize(device)
+    return graph, launches
+
+
+class ProtectedSRGANTrainer(object):
+    """BASELINE config 3: IPR-SRGAN 24 -> 96 (SRResNet + Discriminator96 + VGG content loss, noise-patch trigger,
+    pasted 48 x 48 watermark, SSIM loss, BatchNorm sign loss), GAN phase of experiments/image_super_resolution.py:84-113
+    (``update_g`` then ``update_d`` on the same batch).  The eager step is ~1 400 short launches and host-bound; the
+    whole step -- including the frozen VGG feature extractor, which stays a PyTorch module -- replays as ONE graph."""
+
+    def __init__(self, batch, device, seed=1234, use_graph=True, pretrain=False):
+        self.batch, self.device, self.use_graph, self.pretrain = batch, device, use_graph, pretrain
+        import os
+        os.environ.setdefault("IPR_VGG_RANDOM_INIT", "1")    # no network for pretrained VGG weights (outside the path)
+        torch.manual_seed(seed)
+        model = models.SRGAN(presets.srgan_model(), device=[device])
+        model = models.BlackBoxWrapper(model, presets.srgan_blackbox())
+        self.model = models.WhiteBoxWrapper(model, presets.whitebox("G"))
+        self.low_res = torch.zeros(batch, 3, 24, 24, device=device)
+        self.high_res = torch.zeros(batch, 3, 96, 96, device=device)
+        self.graph, self.launches_per_step = None, None
+
+    def _step(self):
+        m = self.model
+        m.update_g({"low_res": self.low_res, "high_res": self.high_res, "pretrain": self.pretrain})
+        if not self.pretrain:
+            m.update_d({"high_res": m.high_res, "super_res": m.super_res})
+
+    def capture(self, warmup=3):
+        if self.use_graph:
+            self.graph, self.launches_per_step = _capture(self._step, self.device, warmup)
+        else:
+            for _ in range(warmup):
+                before = _lib.launch_count()
+                self._step()
+                self.launches_per_step = _lib.launch_count() - before
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+
+    def step_from_host(self, low_res_cpu, high_res_cpu):
+        """Host batch in, metrics dict out (one step of experiments/image_super_resolution.py's training loop)."""
+        self.low_res.copy_(low_res_cpu, non_blocking=True)
+        self.high_res.copy_(high_res_cpu, non_blocking=True)
+        self.step()
+        return self.model.get_metrics()
+
+
+class ProtectedCycleGANTrainer(object):
+    """BASELINE config 4: IPR-CycleGAN (two Resnet9Blocks generators, two PatchGAN discriminators, InstanceNorm sign
+    loss on GB), one step of experiments/image_translation.py:90-112.  The image-history pools draw from the host RNG
+    (models/util.py:5-35), so the step is TWO graphs -- the generator update and the discriminator update -- with the
+    pool exchange running eagerly between them on static buffers.  The learning rate is a launch argument of the Adam
+    kernel: when the schedulers change it (once per epoch) the graphs are re-captured."""
+
+    def __init__(self, device, size=128, seed=1234, use_graph=True):
+        self.device, self.size, self.use_graph = device, size, use_graph
+        torch.manual_seed(seed)
+        model = models.CycleGAN(presets.cyclegan_model(), device=[device])
+        model = models.BlackBoxWrapper(model, presets.cyclegan_blackbox())
+        self.model = models.WhiteBoxWrapper(model, presets.whitebox("GB"))
+        self.inner = model.model
+        self.real_A = torch.zeros(1, 3, size, size, device=device)
+        self.real_B = torch.zeros(1, 3, size, size, device=device)
+        self.pooled_A = torch.zeros(1, 3, size, size, device=device)
+        self.pooled_B = torch.zeros(1, 3, size, size, device=device)
+        self.graph_g = self.graph_d = None
+        self.launches_per_step = None
+        self._lr = None
+        self.stream = torch.cuda.Stream(device=device)
+
+    def _lrs(self):
+        return (self.inner.optG.param_groups[0]["lr"], self.inner.optD.param_groups[0]["lr"])
+
+    def _step_g(self):
+        self.model.update_g({"real_A": self.real_A, "real_B": self.real_B})
+
+    def _pool(self):
+        m = self.inner
+        self.pooled_A.copy_(m.poolA(m.fake_A))
+        self.pooled_B.copy_(m.poolB(m.fake_B))
+
+    def _step_d(self):
+        self.model.update_d({"real_A": self.real_A, "real_B": self.real_B, "fake_A": self.pooled_A,
+                             "fake_B": self.pooled_B, "pooled": True})
+
+    def _eager(self):
+        self._step_g()
+        self._pool()
+        self._step_d()
+
+    def capture(self, warmup=3):
+        s = self.stream
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                before = _lib.launch_count()
+                self._eager()
+                self.launches_per_step = _lib.launch_count() - before
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        if self.use_graph:
+            # nothing executes during a capture: eager and graph trainers have run the same number of steps afterwards
+            self.graph_g, n_g = _capture(self._step_g, self.device, 0, stream=s)
+            self.graph_d, n_d = _capture(self._step_d, self.device, 0, stream=s)
+            self.launches_per_step = n_g + n_d
+            self._lr = self._lrs()
+
+    def step(self):
+        if self.graph_g is None:
+            return self._eager()
+        if self._lrs() != self._lr:                  # the schedulers moved the learning rate: capture it anew
+            self.capture(warmup=0)
+        self.graph_g.replay()
+        self._pool()
+        self.graph_d.replay()
+
+    def step_from_host(self, real_a_cpu, real_b_cpu):
+        self.real_A.copy_(real_a_cpu, non_blocking=True)
+        self.real_B.copy_(real_b_cpu, non_blocking=True)
+        self.step()
+        return self.model.get_metrics()
