@@ -188,6 +188,7 @@ class ProtectedCycleGANTrainer(object):
         self.graph_g = self.graph_d = None
         self.launches_per_step = None
         self._lr = None
+        self._generated = None
         self.stream = torch.cuda.Stream(device=device)
 
     def _lrs(self):
@@ -198,8 +199,11 @@ class ProtectedCycleGANTrainer(object):
 
     def _pool(self):
         m = self.inner
-        self.pooled_A.copy_(m.poolA(m.fake_A))
-        self.pooled_B.copy_(m.poolB(m.fake_B))
+        # graph mode: the tensors the captured generator update writes (forward_d re-binds m.fake_A / m.fake_B to the
+        # pooled images, and no Python runs during a replay to bind them back)
+        fake_a, fake_b = self._generated if self._generated is not None else (m.fake_A, m.fake_B)
+        self.pooled_A.copy_(m.poolA(fake_a))
+        self.pooled_B.copy_(m.poolB(fake_b))
 
     def _step_d(self):
         self.model.update_d({"real_A": self.real_A, "real_B": self.real_B, "fake_A": self.pooled_A,
@@ -222,7 +226,9 @@ class ProtectedCycleGANTrainer(object):
         torch.cuda.synchronize(self.device)
         if self.use_graph:
             # nothing executes during a capture: eager and graph trainers have run the same number of steps afterwards
+            self._generated = None
             self.graph_g, n_g = _capture(self._step_g, self.device, 0, stream=s)
+            self._generated = (self.inner.fake_A, self.inner.fake_B)
             self.graph_d, n_d = _capture(self._step_d, self.device, 0, stream=s)
             self.launches_per_step = n_g + n_d
             self._lr = self._lrs()
