@@ -66,7 +66,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // timestamps, scripts/tile_phase_probe3.py) -- is the pace maker, and a second CTA doubles the epilogue warps per SM.
 // To fit, the variant keeps 3 smem stages, drains the accumulator 16 columns at a time (half the live registers:
 // <= 102 per thread) and stores rows directly.
-template <int BLOCK_N, int STAGES, int MT, bool RES, int EPI_WARPS, int OCC = 1>
+// TG = 2 ("tile groups"): the 8 epilogue warps form two groups of four that drain ALTERNATE tiles, each group with its
+// own pair of TMEM accumulators (4 in all).  A 128 x 64 tile has a main loop of a few hundred cycles but its read-out
+// (tcgen05.ld of 32 KB, then bias / activation / pack / store at ~0.4 instructions per cycle and scheduler) takes
+// ~1 900 (scripts/tile_phase_probe3.py); with all eight warps on the SAME tile the TMEM read-out and the arithmetic run
+// strictly one after the other.  Two groups on different tiles overlap one group's tcgen05.ld with the other's math.
+template <int BLOCK_N, int STAGES, int MT, bool RES, int EPI_WARPS, int OCC = 1, int TG = 1>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, OCC)
 tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -79,13 +84,17 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
     constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;     // TMEM columns of one accumulator
     constexpr uint32_t BUF_COLS = MT * ACC_COLS;
-    constexpr uint32_t TMEM_COLS = 2 * BUF_COLS;                     // double-buffered: epilogue(i) overlaps mainloop(i+1)
+    constexpr int NBUF = 2 * TG;                                     // accumulators in flight (two per tile group)
+    constexpr uint32_t TMEM_COLS = NBUF * BUF_COLS;                  // multi-buffered: epilogue(i) overlaps mainloop(i+1..)
     static_assert(TMEM_COLS <= 512, "TMEM budget");
+    static_assert(TG == 1 || (EPI_WARPS == 8 && TG == 2 && MT == 1), "tile groups: two groups of four warps");
     constexpr int CH = (BLOCK_N >= 32 && OCC == 1) ? 32 : 16;        // columns per tcgen05.ld
     constexpr int N_CHUNKS = BLOCK_N / CH;
     constexpr int WARP_TMA = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
-    constexpr int EPI_GROUPS = EPI_WARPS / 4;                        // warps per TMEM lane quarter
-    constexpr int EPI_ACTIVE = N_CHUNKS >= EPI_GROUPS ? EPI_WARPS : 4;   // epilogue warps that have columns to drain
+    constexpr int WPG = EPI_WARPS / TG;                              // warps per tile group
+    constexpr int EPI_GROUPS = WPG / 4;                              // warps per TMEM lane quarter (within a tile group)
+    constexpr int EPI_ACTIVE_PG = N_CHUNKS >= EPI_GROUPS ? WPG : 4;  // warps of a group that have columns to drain
+    constexpr int EPI_ACTIVE = TG == 1 ? EPI_ACTIVE_PG : EPI_WARPS;
     constexpr int CH_PER_WARP = N_CHUNKS >= EPI_GROUPS ? N_CHUNKS / EPI_GROUPS : 1;
 
     extern __shared__ uint8_t smem_raw[];
@@ -99,15 +108,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                   : (uint32_t)STAGES * B_STAGE_BYTES;
     const uint32_t bar_full = sB + b_region;                               // STAGES x 8 bytes
     const uint32_t bar_empty = bar_full + STAGES * 8;
-    const uint32_t bar_acc_full = bar_empty + STAGES * 8;                 // 2 x 8
-    const uint32_t bar_acc_empty = bar_acc_full + 16;                     // 2 x 8
-    const uint32_t bar_bres = bar_acc_empty + 16;
+    const uint32_t bar_acc_full = bar_empty + STAGES * 8;                 // NBUF x 8
+    const uint32_t bar_acc_empty = bar_acc_full + NBUF * 8;               // NBUF x 8
+    const uint32_t bar_bres = bar_acc_empty + NBUF * 8;
     const uint32_t tmem_slot = bar_bres + 8;
 
     // per-warp running column statistics [epilogue warp][sum | sumsq][CH_PER_WARP * CH] floats (after the mbarriers)
     float *stat_sm = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * A_BYTES + b_region + 256);
     // per-epilogue-warp staging (2 KB each) for the transposed bf16 store: behind the statistics slots, 16-byte aligned
-    uint8_t *stage_sm = reinterpret_cast<uint8_t *>(stat_sm) + 8 * BLOCK_N * 4;
+    uint8_t *stage_sm = reinterpret_cast<uint8_t *>(stat_sm) + TG * 8 * BLOCK_N * 4;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.dbg && threadIdx.x == 0) {
@@ -123,7 +132,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (warp == WARP_TMA && lane == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, EPI_ACTIVE); }
+        for (int b = 0; b < NBUF; b++) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, EPI_ACTIVE_PG); }
         mbar_init(bar_bres, 1);
         mbar_fence_init();
     }
@@ -185,9 +194,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (RES) { mbar_wait(bar_bres, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
                 const int phase_m = tile / tiles_per_phase;
-                const uint32_t buf = it & 1u;
+                const uint32_t buf = it % NBUF;
                 if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 8 + 0] = clock64();
-                mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+                mbar_wait(bar_acc_empty + 8 * buf, ((it / NBUF) & 1u) ^ 1u);    // epilogue drained this accumulator
                 if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 8 + 1] = clock64();
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * BUF_COLS;
@@ -217,8 +226,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         __syncwarp();
     } else if (warp < EPI_ACTIVE) {
         // ===================== epilogue (warps 0..EPI_ACTIVE-1) =====================
-        const int q = warp & 3;                           // TMEM lane quarter this warp may access
-        const int c_begin = (warp >> 2) * CH_PER_WARP * CH, c_end = c_begin + CH_PER_WARP * CH;   // this warp's columns
+        const int grp = warp / WPG, wg = warp - grp * WPG;   // tile group, warp within the group
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access (WPG is a multiple of 4)
+        const int c_begin = (wg >> 2) * CH_PER_WARP * CH, c_end = c_begin + CH_PER_WARP * CH;   // this warp's columns
         const int row = q * 32 + lane;                    // row of the 128-row tile
         const int per_img = p.tile_h * p.q_w;
         const int i_img = row / per_img, rem_r = row - i_img * per_img;
@@ -232,18 +242,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         uint4 mq0[MQ], mq1[MQ];
         // Tile coordinates advance by gridDim.x every iteration: (phase, m_grp, n_blk) are stepped incrementally and the
         // pixel of a row is (per-tile uniform part) + (per-thread constant part) -- no division in the tile loop.
-        const int g_q = (int)gridDim.x / n_blks, g_r = (int)gridDim.x - g_q * n_blks;
+        const int t_step = TG * (int)gridDim.x;           // a group's next tile
+        const int g_q = t_step / n_blks, g_r = t_step - g_q * n_blks;
         const int tpi_shift = (p.tiles_per_img & (p.tiles_per_img - 1)) == 0 ? 31 - __clz(p.tiles_per_img) : -1;
         const int thr_pix = (i_img * p.out_h + i_row * p.out_sh) * p.out_w + i_col * p.out_sw;
         struct TileIt { int tile, phase, m_grp, n_blk; };
         auto it_init = [&](TileIt &t) {
-            t.tile = blockIdx.x;
+            t.tile = blockIdx.x + grp * gridDim.x;
             t.phase = t.tile / tiles_per_phase;
             const int rm = t.tile - t.phase * tiles_per_phase;
             t.m_grp = rm / n_blks; t.n_blk = rm - t.m_grp * n_blks;
         };
         auto it_next = [&](TileIt &t) {
-            t.tile += gridDim.x; t.n_blk += g_r; t.m_grp += g_q;
+            t.tile += t_step; t.n_blk += g_r; t.m_grp += g_q;
             if (t.n_blk >= n_blks) { t.n_blk -= n_blks; t.m_grp++; }
             while (t.m_grp >= m_groups) { t.m_grp -= m_groups; t.phase++; }
         };
@@ -292,14 +303,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             __syncwarp();
         }
         if (masked) { it_init(wt); w_locate(); w_fetch(mq0); w_fetch(mq1); }
-        uint32_t it = 0;
+        uint32_t it = grp;                                // position in the CTA's tile sequence: grp, grp + TG, ...
         TileIt ct;
         it_init(ct);
-        for (; ct.tile < total_tiles; it_next(ct), it++) {
+        for (; ct.tile < total_tiles; it_next(ct), it += TG) {
             const int phase = ct.phase, m_grp = ct.m_grp, n_blk = ct.n_blk;
-            const uint32_t buf = it & 1u;
+            const uint32_t buf = it % NBUF;
             if (p.dbg && blockIdx.x == 0 && it < 8 && warp == 0 && lane == 0) p.dbg[it * 8 + 3] = clock64();
-            mbar_wait_backoff(bar_acc_full + 8 * buf, (it >> 1) & 1u);
+            mbar_wait_backoff(bar_acc_full + 8 * buf, (it / NBUF) & 1u);
             tc_fence_after();
             if (p.dbg && blockIdx.x == 0 && it < 8 && warp == 0 && lane == 0) p.dbg[it * 8 + 4] = clock64();
 #pragma unroll 1
@@ -473,7 +484,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         if (cta_stats) {
             __syncwarp();
-            float *dst = p.stats + ((size_t)blockIdx.x * 4 + q) * 2 * p.n_total + c_begin;
+            float *dst = p.stats + (((size_t)blockIdx.x * TG + grp) * 4 + q) * 2 * p.n_total + c_begin;
             for (int c = lane; c < CH_PER_WARP * CH; c += 32) {
                 dst[c] = my_stat[c];
                 dst[p.n_total + c] = want_sq ? my_stat[CH_PER_WARP * CH + c] : 0.0f;
@@ -489,16 +500,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
 }
 
-template <int BLOCK_N, int STAGES, int MT, bool RES, int EW, int OCC = 1>
+template <int BLOCK_N, int STAGES, int MT, bool RES, int EW, int OCC = 1, int TG = 1>
 int launch_ew(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3 grid, cudaStream_t st)
 {
     const size_t b_region = RES ? (size_t)p.n_phases * p.n_taps * p.c_chunks * BLOCK_N * BLOCK_K * 2
                                 : (size_t)STAGES * BLOCK_N * BLOCK_K * 2;
-    const size_t smem = (size_t)STAGES * MT * A_STAGE_BYTES + b_region + 256 + 8 * BLOCK_N * 4 + (OCC == 1 ? 8 * 2048 : 0) + 1024 + 64;
+    const size_t smem = (size_t)STAGES * MT * A_STAGE_BYTES + b_region + 256 + TG * 8 * BLOCK_N * 4 + (OCC == 1 ? 8 * 2048 : 0) + 1024 + 64;
     if (smem > (size_t)(OCC == 1 ? 227 : 113) * 1024) return IPR_E_UNSUPPORTED;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (OCC == 1 ? 227 : 113) * 1024);
         if (e != cudaSuccess) return (int)e;
         attr = true;
@@ -506,9 +517,28 @@ int launch_ew(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, d
     const int total = (int)(((grid.x + MT - 1) / MT) * grid.y * grid.z);
     const int slots = ipr_sm_count() * OCC;                                  // persistent: OCC CTAs per SM
     const int ctas = total < slots ? total : slots;
-    IPR_LAUNCH_PDL((tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC>), ctas, 64 + EW * 32, smem, st, ma[0], ma[1], ma[2], ma[3], mb, p);
+    IPR_LAUNCH_PDL((tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC, TG>), ctas, 64 + EW * 32, smem, st, ma[0], ma[1], ma[2], ma[3], mb, p);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
+}
+
+// Two tile groups (TG = 2) where the epilogue does per-element work (the `wide` case below) and every CTA has at least
+// four tiles; same rule in ipr_tapgemm_stats_rows (the per-CTA statistics rows double).
+bool wide_epilogue(const TgParams &p)
+{
+    static const char *force = getenv("IPR_TG_EPI_WARPS");
+    const bool heavy = p.epi_mode == IPR_EPI_BIAS_LRELU || p.epi_mode == IPR_EPI_MASK || p.stats != nullptr;
+    return force ? force[0] == '8' : heavy;
+}
+bool use_tile_groups(const TgParams &p, int block_n, dim3 grid)
+{
+    static const char *off = getenv("IPR_TG_NO_GROUPS");
+    if (off) return false;
+    const long long tiles = (long long)grid.x * grid.y * grid.z;
+    // Measured (scripts/ab_groups.sh, batch 512): the single-k-block patch GEMM gains (32->64 bias+LeakyReLU 46.3 -> 40.6 us);
+    // layers with a real main loop do not (convT4s2 128->64 79 -> 82 us, conv3_dgrad 128->64 44.5 -> 46.6 us), so the
+    // groups are used for main loops of at most two k-blocks.
+    return block_n >= 32 && block_n <= 128 && tiles >= 4LL * ipr_sm_count() && p.n_taps * p.c_chunks <= 2;
 }
 
 // Two CTAs per SM pay off where a tile's main loop is shorter than its epilogue: few k-blocks per tile, enough tiles.
@@ -528,10 +558,13 @@ bool use_two_ctas(const ipr_tapgemm_t *d, const TgParams &p)
 template <int BLOCK_N, int STAGES, int MT, bool RES>
 int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3 grid, cudaStream_t st)
 {
-    static const char *force = getenv("IPR_TG_EPI_WARPS");
-    const bool heavy = p.epi_mode == IPR_EPI_BIAS_LRELU || p.epi_mode == IPR_EPI_MASK || p.stats != nullptr;
-    const bool wide = force ? force[0] == '8' : heavy;
-    if (MT == 1 && wide) return launch_ew<BLOCK_N, STAGES, 1, RES, 8>(ma, mb, p, grid, st);
+    const bool wide = wide_epilogue(p);
+    if (MT == 1 && wide) {
+        if constexpr (BLOCK_N >= 32 && BLOCK_N <= 128) {
+            if (use_tile_groups(p, BLOCK_N, grid)) return launch_ew<BLOCK_N, STAGES, 1, RES, 8, 1, 2>(ma, mb, p, grid, st);
+        }
+        return launch_ew<BLOCK_N, STAGES, 1, RES, 8>(ma, mb, p, grid, st);
+    }
     return launch_ew<BLOCK_N, STAGES, MT, RES, 4>(ma, mb, p, grid, st);
 }
 
@@ -566,8 +599,11 @@ extern "C" int ipr_tapgemm_stats_rows(const ipr_tapgemm_t *d)
     if (rc != IPR_OK) return rc;
     IPR_REQUIRE(d->block_n > 0 && d->n_total % d->block_n == 0 && d->n_phases >= 1, IPR_E_SHAPE);
     const long long tiles = (long long)p.m_tiles * d->n_phases;
+    p.n_taps = d->n_taps; p.c_chunks = (d->a_c + BLOCK_K - 1) / BLOCK_K;
     const long long slots = (long long)ipr_sm_count() * (use_two_ctas(d, p) ? 2 : 1);
-    if (d->n_total == d->block_n) return (int)(4 * (tiles < slots ? tiles : slots));
+    // statistics imply the wide (8-warp) epilogue; with two tile groups every CTA writes 4 rows per group
+    const bool groups = !use_two_ctas(d, p) && use_tile_groups(p, d->block_n, dim3((unsigned)p.m_tiles, 1, (unsigned)d->n_phases));
+    if (d->n_total == d->block_n) return (int)(4 * (groups ? 2 : 1) * (tiles < slots ? tiles : slots));
     return (int)(4 * tiles);
 }
 

@@ -75,6 +75,11 @@ bicubic_kernel(const float *__restrict__ x, float *__restrict__ out, long long p
 constexpr int PDQ_MAX = 64;       // max image edge handled in shared memory
 constexpr int PDQ_THREADS = 256;
 
+// sum / count with the division skipped for count == 1 (x / 1.0f == x exactly): images of 32..128 pixels have a window
+// of ONE, where the filter still has to be executed (its running sum (a + b) - a is not b in floating point) but every
+// IEEE division -- ~25 dependent instructions in a chain only H or W threads of the CTA execute -- is a no-op.
+__device__ __forceinline__ float box_avg(float sum, int cur) { return cur == 1 ? sum : __fdiv_rn(sum, (float)cur); }
+
 // 1-D running-sum box filter with ThreatExchange's window-growth rules; sequential by definition.
 __device__ void box_1d(const float *in, float *out, int n, int stride, int win)
 {
@@ -83,12 +88,12 @@ __device__ void box_1d(const float *in, float *out, int n, int stride, int win)
     int li = 0, ri = 0, oi = 0, cur = 0;
     float sum = 0.0f;
     for (int k = 0; k < n1; k++) { sum = __fadd_rn(sum, in[ri]); cur++; ri += stride; }
-    for (int k = 0; k < n2; k++) { sum = __fadd_rn(sum, in[ri]); cur++; out[oi] = __fdiv_rn(sum, (float)cur); ri += stride; oi += stride; }
+    for (int k = 0; k < n2; k++) { sum = __fadd_rn(sum, in[ri]); cur++; out[oi] = box_avg(sum, cur); ri += stride; oi += stride; }
     for (int k = 0; k < n3; k++) {
         sum = __fadd_rn(sum, in[ri]); sum = __fsub_rn(sum, in[li]);
-        out[oi] = __fdiv_rn(sum, (float)cur); li += stride; ri += stride; oi += stride;
+        out[oi] = box_avg(sum, cur); li += stride; ri += stride; oi += stride;
     }
-    for (int k = 0; k < n4; k++) { sum = __fsub_rn(sum, in[li]); cur--; out[oi] = __fdiv_rn(sum, (float)cur); li += stride; oi += stride; }
+    for (int k = 0; k < n4; k++) { sum = __fsub_rn(sum, in[li]); cur--; out[oi] = box_avg(sum, cur); li += stride; oi += stride; }
 }
 
 __device__ __forceinline__ float to_u8_float(float v) {
@@ -101,8 +106,10 @@ __global__ void __launch_bounds__(PDQ_THREADS)
 pdq_hash_kernel(const float *__restrict__ img, uint32_t *__restrict__ hash, float *__restrict__ coeffs_out,
                 const float *__restrict__ dct, int H, int W)
 {
-    __shared__ float b1[PDQ_MAX * (PDQ_MAX + 1)];
-    __shared__ float b2[PDQ_MAX * (PDQ_MAX + 1)];
+    // the two image planes are sized by the actual image (32 x 32 after up-sampling the 16 x 16 crops: 8.4 KB instead
+    // of 33 KB for the 64 x 64 maximum), which takes the CTAs per SM from 5 to the 8 the thread count allows
+    extern __shared__ float pdq_planes[];
+    float *b1 = pdq_planes, *b2 = pdq_planes + H * (W + 1);
     __shared__ float D[16 * 65];           // padded rows: D[i*65 + k]
     __shared__ float T[16 * 65];           // T[i*65 + j]
     __shared__ float Cf[256];
@@ -133,16 +140,31 @@ pdq_hash_kernel(const float *__restrict__ img, uint32_t *__restrict__ hash, floa
             __syncthreads();
         }
     }
-    // T = D (16x64) * A (64x64), A[k][j] = b1[dec(k)][dec(j)]; sequential k, separately rounded mul and add
-    for (int e = tid; e < 16 * 64; e += PDQ_THREADS) {
-        const int i = e >> 6, j = e & 63;
-        const int jj = (H == 64 && W == 64) ? j : (int)(((j + 0.5) * W) / 64);
-        float s = 0.0f;
+    // T = D (16x64) * A (64x64), A[k][j] = b1[dec(k)][dec(j)]; sequential k, separately rounded mul and add.
+    // The decimation indices int((k + 0.5) * dim / 64) (double arithmetic, as ThreatExchange computes them) are
+    // tabulated once per CTA: evaluating them inside the k loop cost a double-precision divide per multiply-add and
+    // made this kernel ~10x slower than its arithmetic.  Each thread owns column j of rows i0, i0+4, i0+8, i0+12:
+    // four independent accumulation chains share every A[k][j] load.
+    __shared__ int dec_r[64], dec_c[64];
+    if (tid < 64) {
+        const bool full = (H == 64 && W == 64);
+        dec_r[tid] = full ? tid : (int)(((tid + 0.5) * H) / 64);
+        dec_c[tid] = full ? tid : (int)(((tid + 0.5) * W) / 64);
+    }
+    __syncthreads();
+    {
+        const int j = tid & 63, i0 = tid >> 6;
+        const int jj = dec_c[j];
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll 8
         for (int k = 0; k < 64; k++) {
-            const int kk = (H == 64 && W == 64) ? k : (int)(((k + 0.5) * H) / 64);
-            s = __fadd_rn(s, __fmul_rn(D[i * 65 + k], b1[kk * P + jj]));
+            const float a = b1[dec_r[k] * P + jj];
+            s0 = __fadd_rn(s0, __fmul_rn(D[(i0 + 0) * 65 + k], a));
+            s1 = __fadd_rn(s1, __fmul_rn(D[(i0 + 4) * 65 + k], a));
+            s2 = __fadd_rn(s2, __fmul_rn(D[(i0 + 8) * 65 + k], a));
+            s3 = __fadd_rn(s3, __fmul_rn(D[(i0 + 12) * 65 + k], a));
         }
-        T[i * 65 + j] = s;
+        T[(i0 + 0) * 65 + j] = s0; T[(i0 + 4) * 65 + j] = s1; T[(i0 + 8) * 65 + j] = s2; T[(i0 + 12) * 65 + j] = s3;
     }
     __syncthreads();
     // B = T * D^T (16x16)
@@ -214,7 +236,8 @@ extern "C" int ipr_pdq_hash_f32(const float *img, uint32_t *hash, float *coeffs,
     IPR_REQUIRE(batch > 0 && height > 0 && width > 0, IPR_E_SHAPE);
     IPR_REQUIRE(height <= PDQ_MAX && width <= PDQ_MAX && height >= 2 && width >= 2, IPR_E_UNSUPPORTED);
     IPR_REQUIRE(batch < (1LL << 31), IPR_E_UNSUPPORTED);
-    pdq_hash_kernel<<<(unsigned)batch, PDQ_THREADS, 0, ipr_cu(stream)>>>(img, hash, coeffs, dct, height, width);
+    const size_t smem = (size_t)2 * height * (width + 1) * sizeof(float);
+    pdq_hash_kernel<<<(unsigned)batch, PDQ_THREADS, smem, ipr_cu(stream)>>>(img, hash, coeffs, dct, height, width);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
