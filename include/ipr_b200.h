@@ -202,6 +202,8 @@ typedef struct {
     int32_t n_valid;               /* columns >= n_valid are not stored                              */
     float  *stats;                 /* optional [ipr_tapgemm_stats_rows()][2][n_total] partial column sums / sums of
                                       squares; their sum over rows is the statistic (IPR_EPI_MASK: sums only) */
+    const float *scale;            /* optional fp32 [n_total], IPR_EPI_BIAS_LRELU only: out = lrelu(acc / sigma * scale[n] +
+                                      bias[n]) -- an eval-mode BatchNorm (running statistics) folded into its layer */
 } ipr_tapgemm_t;
 
 /* number of M tiles of the launch described by d */

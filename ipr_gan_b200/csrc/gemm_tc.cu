@@ -46,6 +46,7 @@ struct TgParams {
     float slope;
     const float *sigma;
     const float *bias;
+    const float *scale;
     const __nv_bfloat16 *mask;
     void *out;
     int out_h, out_w, out_c, out_sh, out_sw;
@@ -344,6 +345,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 for (int j = 0; j < CH; j++) v[j] = __uint_as_float(raw[j]) * inv_sigma;
 
                 if (p.epi_mode == IPR_EPI_BIAS_LRELU && !(p.dbg_flags & 2)) {
+                    if (p.scale) {                         // eval-mode BatchNorm folded into the layer: per-column factor
+#pragma unroll
+                        for (int j4 = 0; j4 < CH / 4; j4++) {
+                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(p.scale + n0) + j4);
+                            v[4 * j4 + 0] *= s4.x; v[4 * j4 + 1] *= s4.y; v[4 * j4 + 2] *= s4.z; v[4 * j4 + 3] *= s4.w;
+                        }
+                    }
                     if (bias_vec) {                        // 8 broadcast 128-bit loads instead of 32 scalar ones
 #pragma unroll
                         for (int j4 = 0; j4 < CH / 4; j4++) {
@@ -649,7 +657,8 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
         }
         p.out_oh[ph] = d->out_oh[ph]; p.out_ow[ph] = d->out_ow[ph];
     }
-    p.epi_mode = d->epi_mode; p.slope = d->slope; p.sigma = d->sigma; p.bias = d->bias;
+    p.epi_mode = d->epi_mode; p.slope = d->slope; p.sigma = d->sigma; p.bias = d->bias; p.scale = d->scale;
+    IPR_REQUIRE(!d->scale || (d->epi_mode == IPR_EPI_BIAS_LRELU && ipr_aligned16(d->scale)), IPR_E_ALIGN);
     p.mask = (const __nv_bfloat16 *)d->mask; p.out = d->out;
     p.out_h = d->out_h; p.out_w = d->out_w; p.out_c = d->out_c; p.out_sh = d->out_sh; p.out_sw = d->out_sw;
     p.n_valid = d->n_valid > 0 ? d->n_valid : d->n_total; p.stats = d->stats;

@@ -52,7 +52,7 @@ class TapGemm(ctypes.Structure):
         ("out_h", ctypes.c_int32), ("out_w", ctypes.c_int32), ("out_c", ctypes.c_int32),
         ("out_sh", ctypes.c_int32), ("out_sw", ctypes.c_int32),
         ("out_oh", ctypes.c_int8 * MAX_PHASES), ("out_ow", ctypes.c_int8 * MAX_PHASES),
-        ("n_valid", ctypes.c_int32), ("stats", ctypes.c_void_p),
+        ("n_valid", ctypes.c_int32), ("stats", ctypes.c_void_p), ("scale", ctypes.c_void_p),
     ]
 
 
@@ -152,7 +152,7 @@ class Plan(object):
         return a_h, a_w
 
     def run(self, a, b_packed, epi=EPI_LINEAR, slope=0.0, sigma=None, bias=None, mask=None, out=None,
-            want_stats=False, n_valid=None, out_nchw_c=None):
+            want_stats=False, n_valid=None, out_nchw_c=None, scale=None):
         """a: (N, H, W, C) bf16 NHWC.  Returns (out, stats or None)."""
         L = _bind()
         assert a.dtype == torch.bfloat16 and a.is_cuda and a.is_contiguous() and a.dim() == 4
@@ -188,6 +188,8 @@ class Plan(object):
         d.sigma = sigma.data_ptr() if sigma is not None else None
         d.bias = bias.data_ptr() if bias is not None else None
         d.mask = mask.data_ptr() if mask is not None else None
+        d.scale = scale.data_ptr() if scale is not None else None
+        assert scale is None or epi == EPI_BIAS_LRELU
         nv = n_valid or self.cout
         if out is None:
             if epi in (EPI_TANH_NCHW, EPI_LINEAR_NCHW):
