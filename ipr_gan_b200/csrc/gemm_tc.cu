@@ -72,7 +72,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // (tcgen05.ld of 32 KB, then bias / activation / pack / store at ~0.4 instructions per cycle and scheduler) takes
 // ~1 900 (scripts/tile_phase_probe3.py); with all eight warps on the SAME tile the TMEM read-out and the arithmetic run
 // strictly one after the other.  Two groups on different tiles overlap one group's tcgen05.ld with the other's math.
-template <int BLOCK_N, int STAGES, int MT, bool RES, int EPI_WARPS, int OCC = 1, int TG = 1>
+// EPI / ST: the epilogue mode and "column statistics wanted" as COMPILE-TIME values for the hot combinations (-1 = read
+// them from the launch parameters).  The generic epilogue executes ~430 instructions per 32-column chunk, most of them
+// mode dispatch, register moves for the paths not taken and their address arithmetic (ncu source view, profiles/
+// r2_linear_case_full.txt); the low-K layers are paced by exactly that instruction stream.
+template <int BLOCK_N, int STAGES, int MT, bool RES, int EPI_WARPS, int OCC = 1, int TG = 1, int EPI = -1, int ST = -1>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, OCC)
 tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -291,13 +295,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 w_locate();
             }
         };
-        const bool masked = p.epi_mode == IPR_EPI_MASK;
+        const int epi_mode = EPI >= 0 ? EPI : p.epi_mode;
+        const bool has_stats = ST >= 0 ? (ST == 1) : (p.stats != nullptr);
+        const bool masked = epi_mode == IPR_EPI_MASK;
         const bool bias_vec = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;
-        const bool want_sq = p.epi_mode != IPR_EPI_MASK;   // masked data gradients only need column sums (bias grad)
+        const bool want_sq = epi_mode != IPR_EPI_MASK;   // masked data gradients only need column sums (bias grad)
         // column statistics: with a single N block every tile of this CTA covers the same columns, so each warp keeps
         // running sums in its own shared-memory slots (no barrier, fixed order) and writes ONE row at the end:
         // stats rows = 4 * CTAs instead of 4 * tiles.
-        const bool cta_stats = p.stats && n_blks == 1;
+        const bool cta_stats = has_stats && n_blks == 1;
         float *my_stat = stat_sm + warp * 2 * CH_PER_WARP * CH;
         if (cta_stats) {
             for (int c = lane; c < 2 * CH_PER_WARP * CH; c += 32) my_stat[c] = 0.0f;
@@ -342,9 +348,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int n0 = n_blk * BLOCK_N + c0;
                 float v[CH];
 #pragma unroll
-                for (int j = 0; j < CH; j++) v[j] = __uint_as_float(raw[j]) * inv_sigma;
+                for (int j = 0; j < CH; j++) v[j] = __uint_as_float(raw[j]);
+                if (p.sigma) {                             // (uniform) spectral norm: W / sigma applied to the accumulator
+#pragma unroll
+                    for (int j = 0; j < CH; j++) v[j] *= inv_sigma;
+                }
 
-                if (p.epi_mode == IPR_EPI_BIAS_LRELU && !(p.dbg_flags & 2)) {
+                if (epi_mode == IPR_EPI_BIAS_LRELU && !(p.dbg_flags & 2)) {
                     if (p.scale) {                         // eval-mode BatchNorm folded into the layer: per-column factor
 #pragma unroll
                         for (int j4 = 0; j4 < CH / 4; j4++) {
@@ -364,7 +374,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
 #pragma unroll
                     for (int j = 0; j < CH; j++) v[j] = v[j] > 0.0f ? v[j] : v[j] * p.slope;
-                } else if (p.epi_mode == IPR_EPI_MASK) {
+                } else if (epi_mode == IPR_EPI_MASK) {
                     if (valid) {
 #pragma unroll
                         for (int gq = 0; gq < CH / 8; gq++) {
@@ -379,12 +389,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             }
                         }
                     }
-                } else if (p.epi_mode == IPR_EPI_TANH_NCHW) {
+                } else if (epi_mode == IPR_EPI_TANH_NCHW) {
 #pragma unroll
                     for (int j = 0; j < CH; j++) v[j] = tanhf(v[j]);
                 }
 
-                if (p.stats) {
+                if (has_stats) {
                     // per-column sum / sum of squares over this warp's 32 rows: 31-step transposing butterfly
                     float s1[CH], s2[CH];
 #pragma unroll
@@ -425,7 +435,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
 
-                if (p.epi_mode == IPR_EPI_TANH_NCHW || p.epi_mode == IPR_EPI_LINEAR_NCHW) {
+                if (epi_mode == IPR_EPI_TANH_NCHW || epi_mode == IPR_EPI_LINEAR_NCHW) {
                     if (!valid) continue;
                     const size_t hw = (size_t)p.out_h * p.out_w, img = pix / hw, inner = pix - img * hw;
                     float *o = reinterpret_cast<float *>(p.out) + img * p.out_c * hw + inner;
@@ -434,7 +444,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const int n = n0 + j;
                         if (n < p.n_valid) o[(size_t)n * hw] = v[j];
                     }
-                } else if (p.epi_mode == IPR_EPI_LINEAR_F32) {
+                } else if (epi_mode == IPR_EPI_LINEAR_F32) {
                     if (!valid) continue;
                     float *o = reinterpret_cast<float *>(p.out) + pix * p.out_c + n0;
                     if (n0 + CH <= p.n_valid && (p.out_c & 3) == 0) {
@@ -508,7 +518,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
 }
 
-template <int BLOCK_N, int STAGES, int MT, bool RES, int EW, int OCC = 1, int TG = 1>
+template <int BLOCK_N, int STAGES, int MT, bool RES, int EW, int OCC = 1, int TG = 1, int EPI = -1, int ST = -1>
 int launch_ew(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3 grid, cudaStream_t st)
 {
     const size_t b_region = RES ? (size_t)p.n_phases * p.n_taps * p.c_chunks * BLOCK_N * BLOCK_K * 2
@@ -517,7 +527,7 @@ int launch_ew(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, d
     if (smem > (size_t)(OCC == 1 ? 227 : 113) * 1024) return IPR_E_UNSUPPORTED;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC, TG, EPI, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (OCC == 1 ? 227 : 113) * 1024);
         if (e != cudaSuccess) return (int)e;
         attr = true;
@@ -525,7 +535,7 @@ int launch_ew(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, d
     const int total = (int)(((grid.x + MT - 1) / MT) * grid.y * grid.z);
     const int slots = ipr_sm_count() * OCC;                                  // persistent: OCC CTAs per SM
     const int ctas = total < slots ? total : slots;
-    IPR_LAUNCH_PDL((tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC, TG>), ctas, 64 + EW * 32, smem, st, ma[0], ma[1], ma[2], ma[3], mb, p);
+    IPR_LAUNCH_PDL((tapgemm_kernel<BLOCK_N, STAGES, MT, RES, EW, OCC, TG, EPI, ST>), ctas, 64 + EW * 32, smem, st, ma[0], ma[1], ma[2], ma[3], mb, p);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }
@@ -568,6 +578,22 @@ int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3
 {
     const bool wide = wide_epilogue(p);
     if (MT == 1 && wide) {
+        static const char *generic = getenv("IPR_TG_GENERIC_EPI");
+        const bool stats = p.stats != nullptr;
+        if (!generic) {
+            if (p.epi_mode == IPR_EPI_BIAS_LRELU && !stats) {
+                if constexpr (BLOCK_N >= 32 && BLOCK_N <= 128) {
+                    if (use_tile_groups(p, BLOCK_N, grid))
+                        return launch_ew<BLOCK_N, STAGES, 1, RES, 8, 1, 2, IPR_EPI_BIAS_LRELU, 0>(ma, mb, p, grid, st);
+                }
+                return launch_ew<BLOCK_N, STAGES, 1, RES, 8, 1, 1, IPR_EPI_BIAS_LRELU, 0>(ma, mb, p, grid, st);
+            }
+            if (p.epi_mode == IPR_EPI_MASK)
+                return stats ? launch_ew<BLOCK_N, STAGES, 1, RES, 8, 1, 1, IPR_EPI_MASK, 1>(ma, mb, p, grid, st)
+                             : launch_ew<BLOCK_N, STAGES, 1, RES, 8, 1, 1, IPR_EPI_MASK, 0>(ma, mb, p, grid, st);
+            if (p.epi_mode == IPR_EPI_LINEAR && stats)
+                return launch_ew<BLOCK_N, STAGES, 1, RES, 8, 1, 1, IPR_EPI_LINEAR, 1>(ma, mb, p, grid, st);
+        }
         if constexpr (BLOCK_N >= 32 && BLOCK_N <= 128) {
             if (use_tile_groups(p, BLOCK_N, grid)) return launch_ew<BLOCK_N, STAGES, 1, RES, 8, 1, 2>(ma, mb, p, grid, st);
         }
