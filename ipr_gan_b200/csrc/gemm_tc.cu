@@ -317,6 +317,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int phase = ct.phase, m_grp = ct.m_grp, n_blk = ct.n_blk;
             const uint32_t buf = it % NBUF;
             if (p.dbg && blockIdx.x == 0 && it < 8 && warp == 0 && lane == 0) p.dbg[it * 8 + 3] = clock64();
+            // bias (and eval-BatchNorm scale) of the tile's FIRST chunk: fetched before the accumulator wait, so the loads
+            // are in flight while the main loop of this tile still runs (they used to stall the first FADDs)
+            constexpr bool PRE = EPI == IPR_EPI_BIAS_LRELU;     // only where the mode is known at compile time (registers)
+            float4 bpre[PRE ? CH / 4 : 1], spre[PRE ? CH / 4 : 1];
+            const bool pre_bias = PRE && bias_vec;
+            if (pre_bias) {
+#pragma unroll
+                for (int j4 = 0; j4 < (PRE ? CH / 4 : 1); j4++) bpre[j4] = __ldg(reinterpret_cast<const float4 *>(p.bias + n_blk * BLOCK_N + c_begin) + j4);
+                if (p.scale) {
+#pragma unroll
+                    for (int j4 = 0; j4 < (PRE ? CH / 4 : 1); j4++) spre[j4] = __ldg(reinterpret_cast<const float4 *>(p.scale + n_blk * BLOCK_N + c_begin) + j4);
+                }
+            }
             mbar_wait_backoff(bar_acc_full + 8 * buf, (it / NBUF) & 1u);
             tc_fence_after();
             if (p.dbg && blockIdx.x == 0 && it < 8 && warp == 0 && lane == 0) p.dbg[it * 8 + 4] = clock64();
@@ -355,17 +368,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 }
 
                 if (epi_mode == IPR_EPI_BIAS_LRELU && !(p.dbg_flags & 2)) {
+                    const bool first = pre_bias && sub == 0 && c0 == c_begin;
                     if (p.scale) {                         // eval-mode BatchNorm folded into the layer: per-column factor
 #pragma unroll
                         for (int j4 = 0; j4 < CH / 4; j4++) {
-                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(p.scale + n0) + j4);
+                            const float4 s4 = first ? spre[PRE ? j4 : 0] : __ldg(reinterpret_cast<const float4 *>(p.scale + n0) + j4);
                             v[4 * j4 + 0] *= s4.x; v[4 * j4 + 1] *= s4.y; v[4 * j4 + 2] *= s4.z; v[4 * j4 + 3] *= s4.w;
                         }
                     }
                     if (bias_vec) {                        // 8 broadcast 128-bit loads instead of 32 scalar ones
 #pragma unroll
                         for (int j4 = 0; j4 < CH / 4; j4++) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + j4);
+                            const float4 b4 = first ? bpre[PRE ? j4 : 0] : __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + j4);
                             v[4 * j4 + 0] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
                         }
                     } else if (p.bias) {
@@ -598,6 +612,10 @@ int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3
             if (use_tile_groups(p, BLOCK_N, grid)) return launch_ew<BLOCK_N, STAGES, 1, RES, 8, 1, 2>(ma, mb, p, grid, st);
         }
         return launch_ew<BLOCK_N, STAGES, 1, RES, 8>(ma, mb, p, grid, st);
+    }
+    if (MT == 1 && p.stats == nullptr && getenv("IPR_TG_GENERIC_EPI") == nullptr) {       // the light (4-warp) combinations
+        if (p.epi_mode == IPR_EPI_LINEAR) return launch_ew<BLOCK_N, STAGES, 1, RES, 4, 1, 1, IPR_EPI_LINEAR, 0>(ma, mb, p, grid, st);
+        if (p.epi_mode == IPR_EPI_LINEAR_F32) return launch_ew<BLOCK_N, STAGES, 1, RES, 4, 1, 1, IPR_EPI_LINEAR_F32, 0>(ma, mb, p, grid, st);
     }
     return launch_ew<BLOCK_N, STAGES, MT, RES, 4>(ma, mb, p, grid, st);
 }
