@@ -29,12 +29,19 @@ def _prof_begin():
     return ev
 
 
-def _prof_end(kind, flops, start):
+def _prof_end(kind, flops, start, l2_bytes=0.0):
     if start is None:
         return
     ev = torch.cuda.Event(enable_timing=True)
     ev.record()
     PROFILE.append((kind, flops, start, ev))
+    if PROFILE_L2 is not None:
+        PROFILE_L2.append((kind, l2_bytes))
+
+
+# Same order as PROFILE: (kind, bytes the launch's TMA loads pull through L2 into shared memory) -- the operand stream
+# that bounds the low-arithmetic-intensity tiles (every tile re-reads its A box per tap and its B block per k-block).
+PROFILE_L2 = None
 EPI_LINEAR, EPI_BIAS_LRELU, EPI_MASK, EPI_TANH_NCHW, EPI_LINEAR_F32, EPI_LINEAR_NCHW = 0, 1, 2, 3, 4, 5
 
 
@@ -215,8 +222,16 @@ class Plan(object):
         label = "tapgemm:" + self.kind
         if PROFILE_DETAIL:
             label += " %d->%d rows=%d taps=%dx%d bn=%d epi=%d" % (C, self.cout, m_pix, self.n_phases, self.n_taps, block_n, epi)
+        l2 = 0.0
+        if ev is not None:
+            tiles = m_tiles * (self.n_total // block_n) * self.n_phases
+            cw = min(64, C) * 2                                               # bytes of one operand row inside a k-block
+            kb = self.n_taps * ((C + 63) // 64)
+            b_all = self.n_phases * self.n_taps * C * block_n * 2
+            resident = block_n == self.n_total and b_all <= 132 * 1024 and tiles >= 2 * _SM_COUNT
+            l2 = tiles * kb * 128 * cw + (min(tiles, _SM_COUNT) * b_all if resident else tiles * kb * block_n * cw)
         _prof_end(label, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps * self.k_valid() *
-                  getattr(self, "n_valid_flops", nv), ev)
+                  getattr(self, "n_valid_flops", nv), ev, l2)
         return out, stats
 
     def k_valid(self):
@@ -346,8 +361,15 @@ class WGradPlan(object):
         label = "wgrad:" + self.fwd.kind
         if PROFILE_DETAIL:
             label += " %d->%d rows=%d taps=%dx%d splits=%d" % (xc, self.rows, N * d.q_h * d.q_w, self.n_phases, self.n_taps, splits)
+        l2 = 0.0
+        if ev is not None:
+            tiles = L.ipr_wgrad_tiles(ctypes.byref(d))
+            m_blks = max(1, (self.rows + 127) // 128)
+            n_units = self.n_taps * ((xc + 63) // 64)
+            # per 64-pixel k-block: two 8 KB Y boxes per CTA tile, one 8 KB X box per (tap, 64-channel) unit and M block
+            l2 = float(self.n_phases) * kblocks * 8192.0 * (2 * tiles + n_units * m_blks)
         _prof_end(label, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps *
-                  getattr(self, "k_valid_override", xc) * getattr(self, "rows_valid_override", self.rows), ev)
+                  getattr(self, "k_valid_override", xc) * getattr(self, "rows_valid_override", self.rows), ev, l2)
         if self.tap_of is not None:
             check(L.ipr_wgrad_reduce_taps_f32(ws.data_ptr(), splits, self.n_phases, self.rows, self.n_taps, self.x_c,
                                               self.tap_of, self.kk, self.s_n_t, self.s_c_t, grad.data_ptr(),
