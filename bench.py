@@ -19,6 +19,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "IPR-DCGAN 32x32 protected train steps/sec (global batch 512)"
+WORKLOAD = ("IPR-DCGAN 32x32 (ConvGenerator32 + SNDiscriminator32) protected step: TransformDist trigger, 16x16 opaque "
+            "watermark, SSIM loss lambda=1, sign loss gamma0=0.1 'EXAMPLE A'")
 GLOBAL_BATCH = 512
 FLOP_PER_SAMPLE = 2.970e9          # necessary work of one protected step
 
@@ -177,8 +179,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "IPR-DCGAN 32x32 protected step, global batch %d" % args.batch,
-                   "note": "reference CPU path (PyTorch CPU, oracle port pinned to the reference)"},
+        # same workload string and batch keys as the b200 arm (the driver compares the two configs)
+        "config": {"workload": WORKLOAD, "global_batch": args.batch, "per_gpu_batch": args.batch, "parallelism": "cpu",
+                   "note": "reference CPU path (PyTorch CPU, oracle port pinned to the reference), every step a full "
+                           "global-batch step"},
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
                          "sample": "%d steps at batch %d (the metric's global batch) in %.1f s after %d warm-up"
                                    % (steps, sample, dt, warmup)},
@@ -339,8 +343,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "IPR-DCGAN 32x32 (ConvGenerator32 + SNDiscriminator32) protected step: TransformDist "
-                               "trigger, 16x16 opaque watermark, SSIM loss lambda=1, sign loss gamma0=0.1 'EXAMPLE A'",
+        "config": {"workload": WORKLOAD,
                    "global_batch": args.batch, "per_gpu_batch": local_batch, "parallelism": "dp%d" % world,
                    "cuda_graph": not args.no_graph, "l2": "flushed (256 MiB memset) between timed steps",
                    "timing": "sum of per-step CUDA-event times, max over ranks"},
