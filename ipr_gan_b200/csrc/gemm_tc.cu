@@ -613,7 +613,8 @@ int launch(const CUtensorMap *ma, const CUtensorMap &mb, const TgParams &p, dim3
         }
         return launch_ew<BLOCK_N, STAGES, 1, RES, 8>(ma, mb, p, grid, st);
     }
-    if (MT == 1 && p.stats == nullptr && getenv("IPR_TG_GENERIC_EPI") == nullptr) {       // the light (4-warp) combinations
+    static const char *generic_light = getenv("IPR_TG_GENERIC_EPI");
+    if (MT == 1 && p.stats == nullptr && generic_light == nullptr) {       // the light (4-warp) combinations
         if (p.epi_mode == IPR_EPI_LINEAR) return launch_ew<BLOCK_N, STAGES, 1, RES, 4, 1, 1, IPR_EPI_LINEAR, 0>(ma, mb, p, grid, st);
         if (p.epi_mode == IPR_EPI_LINEAR_F32) return launch_ew<BLOCK_N, STAGES, 1, RES, 4, 1, 1, IPR_EPI_LINEAR_F32, 0>(ma, mb, p, grid, st);
     }
@@ -706,8 +707,11 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     p.mask = (const __nv_bfloat16 *)d->mask; p.out = d->out;
     p.out_h = d->out_h; p.out_w = d->out_w; p.out_c = d->out_c; p.out_sh = d->out_sh; p.out_sw = d->out_sw;
     p.n_valid = d->n_valid > 0 ? d->n_valid : d->n_total; p.stats = d->stats;
-    { const char *e = getenv("IPR_TG_DBG_PTR"); p.dbg = e ? (long long *)strtoull(e, nullptr, 0) : nullptr; }
-    { const char *e = getenv("IPR_TG_DBG_FLAGS"); p.dbg_flags = e ? atoi(e) : 0; }
+    // probe switches are read ONCE per process (every getenv walks the whole environment: ~0.5 us each, five per launch)
+    static const char *dbg_ptr = getenv("IPR_TG_DBG_PTR"), *dbg_flags = getenv("IPR_TG_DBG_FLAGS");
+    static const char *env_pair = getenv("IPR_TG_PAIR"), *env_no_res = getenv("IPR_TG_NO_RESIDENT");
+    p.dbg = dbg_ptr ? (long long *)strtoull(dbg_ptr, nullptr, 0) : nullptr;
+    p.dbg_flags = dbg_flags ? atoi(dbg_flags) : 0;
 
     // ---- tensor maps (host-encoded, passed by value as kernel parameters: graph-capturable)
     CUtensorMap ma[4], mb;
@@ -745,12 +749,12 @@ extern "C" int ipr_tapgemm_bf16(const ipr_tapgemm_t *d, ipr_stream_t stream)
     // on B200 it measured no faster (conv3 64->128 @16, batch 512: 590 vs 650 TFLOP/s; step 5.08 vs 5.02 ms) -- with
     // the same 192 KB in flight the per-SM TMA throughput dropped from ~35 to ~24 B/clk.  IPR_TG_PAIR=1 enables it.
     const long long single_tiles = (long long)grid.x * grid.y * grid.z;
-    const bool pair = single_tiles >= 3LL * ipr_sm_count() && getenv("IPR_TG_PAIR") != nullptr && !d->stats;   // stats rows assume MT = 1
+    const bool pair = single_tiles >= 3LL * ipr_sm_count() && env_pair != nullptr && !d->stats;   // stats rows assume MT = 1
     // weights resident in shared memory: one N block, everything (all phases x taps) fits beside 4 A stages, and every
     // CTA has at least two tiles to amortise the one-off weight load over
     const size_t b_all = (size_t)d->n_phases * d->n_taps * p.c_chunks * d->block_n * BLOCK_K * 2;
     const bool resident = d->n_total == d->block_n && b_all <= 132 * 1024 && single_tiles >= 2LL * ipr_sm_count() &&
-                          getenv("IPR_TG_NO_RESIDENT") == nullptr;
+                          env_no_res == nullptr;
     if (!pair && use_two_ctas(d, p)) {
         const bool heavy = p.epi_mode == IPR_EPI_BIAS_LRELU || p.epi_mode == IPR_EPI_MASK || p.stats != nullptr;
         (void)heavy;

@@ -266,7 +266,7 @@ int wgrad_config() {
 // layers -> 4): the kernel is paced by TMA requests per MAC, which fall by 25 % going from N = 128 to N = 192 / 256
 // (measured: 1027 -> 1248 cycles per k-block for twice the MACs), provided no tile is left partly empty.
 int wgrad_x_units(int n_units) {
-    const char *e = getenv("IPR_WGRAD_CFG");
+    static const char *e = getenv("IPR_WGRAD_CFG");
     if (e) { const int c = atoi(e); return c == 2 ? 4 : (c == 3 ? 1 : (c == 4 ? 3 : 2)); }
     if (n_units % 4 == 0) return 4;
     if (n_units % 3 == 0) return 3;
@@ -368,7 +368,7 @@ extern "C" int ipr_wgrad_bf16(const ipr_wgrad_t *d, ipr_stream_t stream)
     p.n_units = d->n_taps * p.x_chunks; p.n_phases = d->n_phases;
     p.kb_per_split = (p.total_kb + d->splits - 1) / d->splits;
     p.ws = d->workspace;
-    { const char *e = getenv("IPR_WGRAD_DBG_PTR"); p.dbg = e ? (long long *)strtoull(e, nullptr, 0) : nullptr; }
+    { static const char *e = getenv("IPR_WGRAD_DBG_PTR"); p.dbg = e ? (long long *)strtoull(e, nullptr, 0) : nullptr; }
     for (int ph = 0; ph < IPR_TG_MAX_PHASES; ph++) {
         p.y_map[ph] = d->y_map[ph];
         for (int t = 0; t < IPR_TG_MAX_TAPS; t++) {

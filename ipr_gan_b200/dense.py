@@ -166,31 +166,42 @@ class Plan(object):
         N, H, W, C = a.shape
         assert C == self.cin, (C, self.cin)
         oh, ow = self.out_hw(H, W)
-        d = TapGemm()
+        # static part of the descriptor (tap tables, phases, strides) is filled once per plan and copied: the per-call
+        # Python cost of the eager paths is dominated by ctypes field stores (up to 200 for a 16-tap layer)
+        tmpl = getattr(self, "_tmpl", None)
+        if tmpl is None:
+            tmpl = TapGemm()
+            tmpl.a_parity = self.a_parity
+            tmpl.n_total, tmpl.n_phases, tmpl.n_taps = self.n_total, self.n_phases, self.n_taps
+            for ph, taps in enumerate(self.taps):
+                for t, (mp, dh, dw, _, _) in enumerate(taps):
+                    tmpl.tap_map[ph][t], tmpl.tap_dh[ph][t], tmpl.tap_dw[ph][t] = mp, dh, dw
+                tmpl.out_oh[ph], tmpl.out_ow[ph] = self.out_o[ph]
+            tmpl.out_sh = tmpl.out_sw = self.out_s
+            self._tmpl = tmpl
+        d = TapGemm.from_buffer_copy(tmpl)
         d.a, d.a_n, d.a_h, d.a_w, d.a_c = a.data_ptr(), N, H, W, C
-        d.a_parity = self.a_parity
         d.q_h, d.q_w = (H // 2, W // 2) if self.a_parity else (H, W)
         # tile width: the kernel is paced by TMA row requests (128 A rows + BLOCK_N B rows per k-block and tile) and runs
         # one persistent CTA per SM, so pick the N tile that minimises  waves(tiles / SMs) * (128 + BLOCK_N)
         m_pix = N * ((H // 2) * (W // 2) if self.a_parity else H * W)
         m_tiles = (m_pix + 127) // 128
         block_n, best = self.block_n, None
-        bn = self.block_n
+        cache = self.__dict__.setdefault("_bn_cache", {})
+        bn = self.block_n if (m_tiles, C) not in cache else 0
+        if bn == 0:
+            block_n = cache[(m_tiles, C)]
         while bn >= 16:
             if self.n_total % bn == 0:
                 tiles = m_tiles * (self.n_total // bn) * self.n_phases
                 b_all = self.n_phases * self.n_taps * C * bn * 2
-                resident = bn == self.n_total and b_all <= 132 * 1024 and tiles >= 2 * _SM_COUNT   # weights stay in smem
-                cost = -(-tiles // _SM_COUNT) * (128 + (0 if resident else bn)) * (1.0 if bn >= 64 else 1.5)
+                resident = bn == self.n_total and b_all <= 132 * 1024 and tiles >= 2 * _sm_count()   # weights stay in smem
+                cost = -(-tiles // _sm_count()) * (128 + (0 if resident else bn)) * (1.0 if bn >= 64 else 1.5)
                 if best is None or cost < best:
                     best, block_n = cost, bn
             bn //= 2
-        d.b, d.n_total, d.block_n = b_packed.data_ptr(), self.n_total, block_n
-        d.n_phases, d.n_taps = self.n_phases, self.n_taps
-        for ph, taps in enumerate(self.taps):
-            for t, (mp, dh, dw, _, _) in enumerate(taps):
-                d.tap_map[ph][t], d.tap_dh[ph][t], d.tap_dw[ph][t] = mp, dh, dw
-            d.out_oh[ph], d.out_ow[ph] = self.out_o[ph]
+        cache[(m_tiles, C)] = block_n
+        d.b, d.block_n = b_packed.data_ptr(), block_n
         d.epi_mode, d.slope = epi, float(slope)
         d.sigma = sigma.data_ptr() if sigma is not None else None
         d.bias = bias.data_ptr() if bias is not None else None
@@ -207,7 +218,6 @@ class Plan(object):
                 out = torch.empty(N, oh, ow, nv, device=a.device, dtype=torch.bfloat16)
         d.out, d.out_h, d.out_w = out.data_ptr(), oh, ow
         d.out_c = out.shape[1] if epi in (EPI_TANH_NCHW, EPI_LINEAR_NCHW) else out.shape[3]
-        d.out_sh = d.out_sw = self.out_s
         d.n_valid = nv
         stats = None
         if want_stats:
@@ -228,8 +238,8 @@ class Plan(object):
             cw = min(64, C) * 2                                               # bytes of one operand row inside a k-block
             kb = self.n_taps * ((C + 63) // 64)
             b_all = self.n_phases * self.n_taps * C * block_n * 2
-            resident = block_n == self.n_total and b_all <= 132 * 1024 and tiles >= 2 * _SM_COUNT
-            l2 = tiles * kb * 128 * cw + (min(tiles, _SM_COUNT) * b_all if resident else tiles * kb * block_n * cw)
+            resident = block_n == self.n_total and b_all <= 132 * 1024 and tiles >= 2 * _sm_count()
+            l2 = tiles * kb * 128 * cw + (min(tiles, _sm_count()) * b_all if resident else tiles * kb * block_n * cw)
         _prof_end(label, 2.0 * N * d.q_h * d.q_w * self.n_phases * self.n_taps * self.k_valid() *
                   getattr(self, "n_valid_flops", nv), ev, l2)
         return out, stats
@@ -253,7 +263,18 @@ class WGrad(ctypes.Structure):
     ]
 
 
-_SM_COUNT = 148
+_SM_COUNT_CACHE = []
+
+
+def _sm_count():
+    """SMs of the current device (148 on B200), as the C side's ipr_sm_count() sees them; 148 without a device
+    (host-logic tests of the planning code)."""
+    if not _SM_COUNT_CACHE:
+        n = 148
+        if torch.cuda.is_available():
+            n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        _SM_COUNT_CACHE.append(n)
+    return _SM_COUNT_CACHE[0]
 _WGRAD_OVERSUB = int(__import__('os').environ.get('IPR_WGRAD_OVERSUB', '1'))
 
 
@@ -333,24 +354,29 @@ class WGradPlan(object):
         assert grad.dtype == torch.float32 and grad.is_contiguous()
         N, xh, xw, xc = x.shape
         assert xc == self.x_c and y.shape[3] == self.rows, (x.shape, y.shape, self.x_c, self.rows)
-        d = WGrad()
-        d.y, d.y_c, d.y_parity = y.data_ptr(), y.shape[3], self.y_parity
-        d.x, d.x_c, d.x_parity = x.data_ptr(), xc, self.x_parity
+        tmpl = getattr(self, "_tmpl", None)
+        if tmpl is None:                             # static part of the descriptor, filled once (see Plan.run)
+            tmpl = WGrad()
+            tmpl.y_parity, tmpl.x_parity = self.y_parity, self.x_parity
+            tmpl.n_phases, tmpl.n_taps = self.n_phases, self.n_taps
+            for ph, taps in enumerate(self.fwd.taps):
+                for t, (mp, dh, dw, _, _) in enumerate(taps):
+                    tmpl.tap_map[ph][t], tmpl.tap_dh[ph][t], tmpl.tap_dw[ph][t] = mp, dh, dw
+                tmpl.y_map[ph] = (2 * self.fwd.out_o[ph][0] + self.fwd.out_o[ph][1]) if self.y_parity else 0
+            self._tmpl = tmpl
+        d = WGrad.from_buffer_copy(tmpl)
+        d.y, d.y_c = y.data_ptr(), y.shape[3]
+        d.x, d.x_c = x.data_ptr(), xc
         d.n_imgs = N
         d.q_h, d.q_w = (xh // 2, xw // 2) if self.x_parity else (xh, xw)
-        d.n_phases, d.n_taps = self.n_phases, self.n_taps
-        for ph, taps in enumerate(self.fwd.taps):
-            for t, (mp, dh, dw, _, _) in enumerate(taps):
-                d.tap_map[ph][t], d.tap_dh[ph][t], d.tap_dw[ph][t] = mp, dh, dw
-            d.y_map[ph] = (2 * self.fwd.out_o[ph][0] + self.fwd.out_o[ph][1]) if self.y_parity else 0
         kblocks = L.ipr_wgrad_total_kblocks(ctypes.byref(d))
         if kblocks < 0:
             check(kblocks, "ipr_wgrad_total_kblocks")
         if splits is None:
             tiles = L.ipr_wgrad_tiles(ctypes.byref(d))           # one CTA per SM (48 KB stages): fill the chip once
             # one CTA per SM (about 190 KB of smem stages): never exceed one wave, a second partial wave doubles the time
-            slots = _SM_COUNT * _WGRAD_OVERSUB
-            splits = max(1, min(kblocks // 4 if kblocks >= 8 else 1, slots // tiles, _SM_COUNT))
+            slots = _sm_count() * _WGRAD_OVERSUB
+            splits = max(1, min(kblocks // 4 if kblocks >= 8 else 1, slots // tiles, _sm_count()))
         d.splits = splits
         nbytes = L.ipr_wgrad_workspace_bytes(ctypes.byref(d))
         ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
