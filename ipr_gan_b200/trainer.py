@@ -9,11 +9,23 @@ experiments/image_generation.py:38-84), plus the two B200-specific pieces around
   ``optimizer.step()`` (``dist.AllReduceOptimizer``), BatchNorm statistics stay per rank exactly like the
   reference's ``nn.DataParallel`` replicas (experiments/base.py:36-39).
 """
+import contextlib
+
 import torch
 
 import ipr_gan_b200
 
 ipr_gan_b200.enable_dropin()
+
+
+@contextlib.contextmanager
+def _nvtx(name):
+    """NVTX range around a step (tracing) -- shows up in nsys / ncu timelines; ~1 us."""
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 import models  # noqa: E402
 from configs import presets  # noqa: E402
@@ -81,6 +93,10 @@ class ProtectedDCGANTrainer(object):
 
     def step(self):
         """One training step on the current contents of the device buffers."""
+        with _nvtx("ipr.dcgan.step"):
+            self._step_or_replay()
+
+    def _step_or_replay(self):
         if self.graph is not None:
             self.graph.replay()
             board = self.model.board
@@ -154,10 +170,11 @@ class ProtectedSRGANTrainer(object):
                 self.launches_per_step = _lib.launch_count() - before
 
     def step(self):
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self._step()
+        with _nvtx("ipr.srgan.step"):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._step()
 
     def step_from_host(self, low_res_cpu, high_res_cpu):
         """Host batch in, metrics dict out (one step of experiments/image_super_resolution.py's training loop)."""
@@ -238,9 +255,10 @@ class ProtectedCycleGANTrainer(object):
             return self._eager()
         if self._lrs() != self._lr:                  # the schedulers moved the learning rate: capture it anew
             self.capture(warmup=0)
-        self.graph_g.replay()
-        self._pool()
-        self.graph_d.replay()
+        with _nvtx("ipr.cyclegan.step"):
+            self.graph_g.replay()
+            self._pool()
+            self.graph_d.replay()
 
     def step_from_host(self, real_a_cpu, real_b_cpu):
         self.real_A.copy_(real_a_cpu, non_blocking=True)
