@@ -369,24 +369,39 @@ class _SeqFn(torch.autograd.Function):
                     gamma_g = None
                 else:
                     gamma_g = gamma
-                dg = torch.empty_like(gamma) if gamma_g is not None else None
-                db = torch.empty_like(gamma) if gamma_g is not None else None
+                # gamma / beta gradients go straight into the parameters' bound ``.grad`` views (the kernel accumulates)
+                # when both have one; otherwise into fresh buffers that are handed to autograd below
+                dg = db = None
+                direct = False
+                if gamma_g is not None:
+                    dst_g, acc_g, _ = engine._grad_dst(nm.weight)
+                    dst_b, acc_b, _ = engine._grad_dst(nm.bias)
+                    direct = acc_g and acc_b
+                    dg, db = (dst_g, dst_b) if direct else (torch.empty_like(gamma), torch.empty_like(gamma))
                 sg, g0, sc = (None, 0.0, 0.0)
                 if hook is not None and gamma_g is not None:
                     # white-box sign loss (tools/sign_model.py:42-49): d/dgamma is added inside this launch, once per
                     # armed step and layer (models/protect.py: _SignHook)
                     sg, g0, sc = hook(P.norm_index[id(nm)])
                 slope_ptr = b.prelu.weight.detach() if b.prelu is not None else None
-                dsl = torch.empty_like(slope_ptr) if (slope_ptr is not None and not skip_params) else None
+                dsl, dsl_direct = None, False
+                if slope_ptr is not None and not skip_params:
+                    dst_s, acc_s, _ = engine._grad_dst(b.prelu.weight)
+                    # one accumulate flag per launch: the slope gradient shares it with gamma / beta
+                    dsl_direct = acc_s and (direct or gamma_g is None)
+                    dsl = dst_s if dsl_direct else torch.empty_like(slope_ptr)
+                accumulate = 1 if (direct or (gamma_g is None and dsl_direct)) else 0
+                if accumulate and dsl is not None and not dsl_direct:
+                    dsl.zero_()                       # (mixed case: the launch accumulates, this buffer is fresh)
                 check(lib().ipr_norm_bwd_bf16(_p(dz), _p(y0), _p(dy0), rec["groups"], rec["rows"], b.n_p,
                                               rec["has_norm"], _p(gamma), _p(rec["scale"]), _p(rec["shift"]),
-                                              _p(rec["mean"]), _p(rec["rstd"]), _p(dg), _p(db), 0, _p(sg), float(g0),
-                                              float(sc), b.act, float(b.slope), _p(slope_ptr), _p(dsl), _p(ws), nbytes,
-                                              _st()), "ipr_norm_bwd_bf16")
-                if gamma_g is not None:
+                                              _p(rec["mean"]), _p(rec["rstd"]), _p(dg), _p(db), accumulate, _p(sg),
+                                              float(g0), float(sc), b.act, float(b.slope), _p(slope_ptr), _p(dsl), _p(ws),
+                                              nbytes, _st()), "ipr_norm_bwd_bf16")
+                if gamma_g is not None and not direct:
                     give(nm.weight, lambda dst, acc, v=dg: dst.add_(v) if acc else dst.copy_(v))
                     give(nm.bias, lambda dst, acc, v=db: dst.add_(v) if acc else dst.copy_(v))
-                if dsl is not None:
+                if dsl is not None and not dsl_direct:
                     give(b.prelu.weight, lambda dst, acc, v=dsl: dst.add_(v) if acc else dst.copy_(v))
             dy2 = dy0.view(M, 1, 1, b.n_p)
             # bias and weight gradients
@@ -394,6 +409,9 @@ class _SeqFn(torch.autograd.Function):
                 pass
             elif b.conv.bias is not None:
                 def _bias(dst, acc, dy2=dy2, b=b):
+                    if b.n_p == b.cout:               # no channel padding: the column sums land in the gradient itself
+                        engine.colsum_bf16(dy2.view(M, b.n_p), out=dst, accumulate=acc)
+                        return
                     full = engine.colsum_bf16(dy2.view(M, b.n_p))
                     if acc:
                         dst.add_(full[:b.cout])
