@@ -33,6 +33,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="global batch (default: the metric's 512)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pinned-inputs", action="store_true",
+                    help="e2e: copy the batch in front of the graph replay instead of inside the graph")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-eager-baseline", action="store_true")
     ap.add_argument("--device-latents", action="store_true", help="draw latents on the device instead of copying them")
@@ -226,10 +228,14 @@ def run_b200(args):
 
     from ipr_gan_b200 import dense
     from ipr_gan_b200.trainer import ProtectedDCGANTrainer
-    tr = ProtectedDCGANTrainer(local_batch, device, use_graph=not args.no_graph, device_latents=args.device_latents)
+    tr = ProtectedDCGANTrainer(local_batch, device, use_graph=not args.no_graph, device_latents=args.device_latents,
+                               pinned_inputs=not args.no_pinned_inputs)
     gen = torch.Generator().manual_seed(1234 + rank)
-    real_h = torch.randn(local_batch, 3, 32, 32, generator=gen).clamp(-1, 1).pin_memory()
-    z_h = torch.randn(local_batch, 128, generator=gen).pin_memory()
+    # the batch lives in the trainer's own pinned buffers, where a data loader would put it; every e2e step copies it
+    # host -> device again (graph memcpy nodes when pinned_inputs, cudaMemcpyAsync in front of the replay otherwise)
+    real_h, z_h = tr.real_host, tr.latent_host
+    real_h.copy_(torch.randn(local_batch, 3, 32, 32, generator=gen).clamp(-1, 1))
+    z_h.copy_(torch.randn(local_batch, 128, generator=gen))
     _dbg('trainer built')
     tr.set_inputs(real_h, z_h)
     tr.capture()
@@ -351,6 +357,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "steps/s",
                 "h2d_bytes_per_step": int(real_h.numel() * 4 + (0 if args.device_latents else z_h.numel() * 4)) * world,
                 "d2h_bytes_per_step": 8 * 4 * world, "wall_s": wall_e2e,
+                "input_copies": "inside the step graph, image copy overlapped with G(z)" if tr.graph_pinned is not None else "cudaMemcpyAsync in front of the graph replay",
                 "call": "ProtectedDCGANTrainer.step_from_host(real_cpu, latent_cpu) -> metrics dict (one 32-byte "
                         "board copy per rank; the values are already reduced over the ranks on the device)",
                 "latents": "device (Philox)" if args.device_latents else "host randn, copied every step"},

@@ -34,9 +34,15 @@ from ipr_gan_b200 import _lib, engine  # noqa: E402
 
 class ProtectedDCGANTrainer(object):
     def __init__(self, batch, device, seed=1234, fn_inp="TransformDist", use_graph=True, size=32,
-                 device_latents=False):
+                 device_latents=False, pinned_inputs=False):
         self.batch, self.device, self.use_graph = batch, device, use_graph
         self.device_latents = device_latents
+        # pinned_inputs: a second graph whose first nodes are the host->device copies of the step's batch out of the
+        # trainer's own pinned buffers (``real_host`` / ``latent_host``, which a data loader fills in place): the image
+        # copy runs on a copy stream that only D(real) waits for, so it overlaps G(z) instead of preceding the step
+        self.pinned_inputs = bool(pinned_inputs and use_graph)
+        self.graph_pinned = None
+        self._copy_stream = torch.cuda.Stream(device=device) if self.pinned_inputs else None
         torch.manual_seed(seed)                      # identical initial replicas on every rank
         mcfg = presets.dcgan_model(size)
         if use_graph:
@@ -62,6 +68,22 @@ class ProtectedDCGANTrainer(object):
             self.normal.fill_(self.latent)
         self.model.update_d({"real_sample": self.real, "latent": self.latent})
         self.model.update_g({"fake_sample": self.model.fake_sample})
+
+    def _step_from_pinned(self):
+        """The step preceded by its own input copies (captured as the ``graph_pinned`` variant)."""
+        dev = self.device
+        main, cs = torch.cuda.current_stream(dev), self._copy_stream
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            self.real.copy_(self.real_host, non_blocking=True)
+        if self.normal is None:
+            self.latent.copy_(self.latent_host, non_blocking=True)      # G(z) needs it first: main stream
+        if engine.concurrent_passes():
+            engine.aux_stream(dev).wait_stream(cs)   # D(real) runs there (models/dcgan.py forward_d): only it waits
+        else:
+            main.wait_stream(cs)
+        self._step()
+        main.wait_stream(cs)                         # every forked stream rejoins before the capture ends
 
     def set_inputs(self, real, latent):
         """Stage a host (or device) batch into the static device buffers (async when the source is pinned)."""
@@ -90,6 +112,12 @@ class ProtectedDCGANTrainer(object):
             self._step()
             self.launches_per_step = _lib.launch_count() - before
         torch.cuda.synchronize(self.device)
+        if self.pinned_inputs:
+            engine.reset_caches()
+            self.graph_pinned = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_pinned, stream=s, capture_error_mode="thread_local"):
+                self._step_from_pinned()
+            torch.cuda.synchronize(self.device)
 
     def step(self):
         """One training step on the current contents of the device buffers."""
@@ -108,6 +136,18 @@ class ProtectedDCGANTrainer(object):
     def step_from_host(self, real_cpu, latent_cpu=None):
         """The call a user of the reference makes (experiments/image_generation.py:92-101): host tensors in,
         metrics dict (Python floats) out.  With ``device_latents`` the latent argument is not needed."""
+        if self.graph_pinned is not None:
+            # batches normally arrive IN the pinned buffers (no host copy); anything else is staged through them.  The
+            # previous step's copies have completed: every call ends with the metrics read-back.
+            if real_cpu.data_ptr() != self.real_host.data_ptr():
+                self.real_host.copy_(real_cpu)
+            if latent_cpu is not None and latent_cpu.data_ptr() != self.latent_host.data_ptr():
+                self.latent_host.copy_(latent_cpu)
+            with _nvtx("ipr.dcgan.step"):
+                self.graph_pinned.replay()
+                if self.model.board is not None:
+                    self.model.board.touch()
+            return self.model.get_metrics()
         self.set_inputs(real_cpu, latent_cpu)
         self.step()
         return self.model.get_metrics()

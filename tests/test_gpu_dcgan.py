@@ -320,3 +320,29 @@ def test_packed_weights_follow_the_masters():
         Go.convs[3].weight[:, 0] = 0.0
     out = G(z.cuda())
     assert float(out[:, 0].abs().max()) == 0.0 and rel(out, Go(z)) < 4e-2
+
+
+def test_pinned_input_graph_equals_plain_graph():
+    """``pinned_inputs=True`` captures a second graph whose first nodes copy the batch out of the trainer's pinned host
+    buffers (the image copy on its own stream, overlapping G(z)): same metrics and parameters, bit for bit, as staging
+    the batch in front of the plain graph."""
+    from ipr_gan_b200.trainer import ProtectedDCGANTrainer
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(21)
+    warm = (torch.randn(32, 3, 32, 32, generator=g).clamp(-1, 1), torch.randn(32, 128, generator=g))
+    batches = [(torch.randn(32, 3, 32, 32, generator=g).clamp(-1, 1), torch.randn(32, 128, generator=g)) for _ in range(3)]
+
+    def run(pinned):
+        tr = ProtectedDCGANTrainer(32, dev, use_graph=True, pinned_inputs=pinned)
+        tr.set_inputs(*warm)
+        tr.real_host.copy_(warm[0]); tr.latent_host.copy_(warm[1])
+        tr.capture(warmup=3)
+        assert (tr.graph_pinned is not None) == pinned
+        out = [tr.step_from_host(real, z) for real, z in batches]
+        torch.cuda.synchronize()
+        return out, [p.detach().clone() for p in list(tr.model.G.parameters()) + list(tr.model.D.parameters())]
+
+    m0, p0 = run(False)
+    m1, p1 = run(True)
+    assert m0 == m1, (m0, m1)
+    assert all(torch.equal(a, b) for a, b in zip(p0, p1))
