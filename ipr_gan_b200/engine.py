@@ -416,39 +416,65 @@ _SIDE_STREAMS = {}
 _USE_SIDE = os.environ.get("IPR_SIDE_STREAM", "1") != "0"
 
 
+N_SIDE = max(1, int(os.environ.get("IPR_SIDE_STREAMS", "4")))
+
+
 class _Fork(object):
-    """Runs the weight-gradient GEMMs (and their split-K reductions / bias column sums) of a backward pass on a side
-    stream so that they overlap the data-gradient chain, which is the critical path.  Works the same eagerly and
-    under stream capture (the waits become graph edges).  Tensors handed to the side stream are kept alive until
-    ``join`` so the caching allocator cannot recycle them while the side stream still reads them."""
+    """Runs the weight-gradient GEMMs (and their split-K reductions / bias column sums) of a backward pass on side
+    streams so that they overlap the data-gradient chain.  Works the same eagerly and under stream capture (the waits
+    become graph edges).  Tensors handed to a side stream are kept alive until ``join`` so the caching allocator cannot
+    recycle them while that stream still reads them.
+
+    There are ``N_SIDE`` side streams per device and every piece of work carries a ``key`` (its layer): work of one
+    layer always lands on the same stream, so accumulations into that layer's slice of the gradient arena stay ordered
+    -- also between two passes that back-propagate concurrently (D(real) / D(fake), adversarial / trigger pass) --
+    while different layers proceed in parallel.  With ONE side stream the ~24 weight-gradient GEMMs and their ~24
+    reductions of a step formed the longest dependency chain of the captured graph at 64 samples per GPU
+    (scripts/graph_critical_path.py: 0.8 of 1.58 ms)."""
 
     def __init__(self, device):
         self.enabled = _USE_SIDE
         if not self.enabled:
             return
         self.main = torch.cuda.current_stream(device)
-        key = (device.index if device.index is not None else torch.cuda.current_device())
-        if key not in _SIDE_STREAMS:
-            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-        self.side = _SIDE_STREAMS[key]
+        d = device.index if device.index is not None else torch.cuda.current_device()
+        self.sides = []
+        for k in range(N_SIDE):
+            key = d if k == 0 else ("side", d, k)
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+            self.sides.append(_SIDE_STREAMS[key])
         self.keep = []
-        self.used = False
+        self.used = set()
 
-    def run(self, fn, *tensors):
+    def run(self, fn, *tensors, key=0):
         if not self.enabled:
             return fn()
-        self.side.wait_stream(self.main)            # everything enqueued so far happens-before the side work
-        with torch.cuda.stream(self.side):
+        k = key % len(self.sides)
+        side = self.sides[k]
+        side.wait_stream(self.main)                 # everything enqueued so far happens-before the side work
+        with torch.cuda.stream(side):
             r = fn()
         self.keep.extend(tensors)
-        self.used = True
+        self.used.add(k)
         return r
+
+    def run_after_all(self, fn, *tensors):
+        """Work that consumes the results of every side stream (the spectral-norm weight-gradient transform)."""
+        if not self.enabled:
+            return fn()
+        first = self.sides[0]
+        for k in sorted(self.used):
+            if k != 0:
+                first.wait_stream(self.sides[k])
+        return self.run(fn, *tensors, key=0)
 
     def join(self):
         if self.enabled and self.used:
-            self.main.wait_stream(self.side)
+            for k in sorted(self.used):
+                self.main.wait_stream(self.sides[k])
             self.keep = []
-            self.used = False
+            self.used = set()
 
 
 def _grad_dst(param):
@@ -552,7 +578,7 @@ class _GeneratorFn(torch.autograd.Function):
         mod_c = module.convs
         fork = _Fork(dev)
         dw4, acc4, ret4 = _grad_dst(mod_c[3].weight)
-        fork.run(lambda: P.last_wg.run(acts[3], col, dw4, accumulate=acc4), col, dw4)
+        fork.run(lambda: P.last_wg.run(acts[3], col, dw4, accumulate=acc4), col, dw4, key=0)
         d_act, _ = P.last_dg.run(col, P.packs.get("ct3_dg"))
         dws, dgs, dbs = [None] * 3, [None] * 3, [None] * 3
         sign_hook = getattr(module, "_ipr_sign_hook", None)
@@ -574,7 +600,8 @@ class _GeneratorFn(torch.autograd.Function):
             dx = bn_relu_bwd(d_act, raws[i], scales[i], shifts[i], gammas[i], means[i], rstds[i], dg_t, db_t,
                              2 if acc_g else 0, sg, g0, sc)
             dw_t, acc_w, dws[i] = _grad_dst(mod_c[i][0].weight)
-            fork.run(lambda i=i, dx=dx, dw_t=dw_t, acc_w=acc_w: P.ct_wg[i].run(dx, acts[i], dw_t, accumulate=acc_w), dx, dw_t)
+            fork.run(lambda i=i, dx=dx, dw_t=dw_t, acc_w=acc_w: P.ct_wg[i].run(dx, acts[i], dw_t, accumulate=acc_w), dx, dw_t,
+                     key=1 + i)
             wd = P.packs.get("ct%d_dg" % i)
             if i > 0:
                 d_act, _ = P.ct_dg[i].run(dx, wd)
@@ -582,7 +609,7 @@ class _GeneratorFn(torch.autograd.Function):
                 d_act, _ = P.ct_dg[i].run(dx, wd, epi=dense.EPI_MASK, slope=0.0, mask=acts[0])
         dh = d_act.view(B, 1, 1, -1)
         dfc_t, acc_fc, dfc_w = _grad_dst(module.fc[0].weight)
-        fork.run(lambda: P.fc_wg.run(dh, a0, dfc_t, accumulate=acc_fc), dh, dfc_t)
+        fork.run(lambda: P.fc_wg.run(dh, a0, dfc_t, accumulate=acc_fc), dh, dfc_t, key=4)
         perm = P.perm_on(dev)
         db_t, acc_fb, dfc_b = _grad_dst(module.fc[0].bias)
         colsum_bf16(dh.view(B, -1), out=db_t, accumulate=2 if acc_fb else 0, out_index=perm)
@@ -683,26 +710,27 @@ class _DiscriminatorFn(torch.autograd.Function):
         fork = _Fork(dev)
         if want:
             dst, acc, gB[6] = _grad_dst(layers[6].bias)
-            fork.run(lambda dy=dy, dst=dst, acc=acc: colsum_bf16(dy.view(-1, dy.shape[-1]), out=dst, accumulate=acc), dy, dst)
+            fork.run(lambda dy=dy, dst=dst, acc=acc: colsum_bf16(dy.view(-1, dy.shape[-1]), out=dst, accumulate=acc), dy, dst,
+                     key=0)
         for i in range(5, -1, -1):                 # conv layers 7..2 (index i+1 in the layer list)
             li = i + 1
             if want:
                 gW[li] = torch.empty_like(ws[li])
-                fork.run(lambda i=i, dy=dy, g=gW[li]: P.conv_wg[i].run(dy, acts[i], g), dy)
+                fork.run(lambda i=i, dy=dy, g=gW[li]: P.conv_wg[i].run(dy, acts[i], g), dy, key=1 + i)
             # the data-gradient GEMM's epilogue also yields the column sums of its output = the bias gradient below
             dy, st = P.conv_dg[i].run(dy, P.packs.get("c%d_dg" % li), epi=dense.EPI_MASK, slope=0.1, mask=acts[i],
                                       sigma=sig[li], want_stats=want)
             if want:
                 dst, acc, gB[i] = _grad_dst(layers[i].bias)
                 fork.run(lambda st=st, dst=dst, acc=acc, n=dy.shape[-1]: colsum_partials(st, out=dst, accumulate=acc, ncols=n),
-                         st, dst)
+                         st, dst, key=2 + i)
         dx = None
         if ctx.x_needs_grad:
             t9, _ = P.first_dg.run(dy, P.packs.get("c0_dg"), epi=dense.EPI_LINEAR_F32, sigma=sig[0], n_valid=32)
             dx = col2im3(t9, False)
         if want:
             gW[0] = torch.empty_like(ws[0])
-            fork.run(lambda: P.first_wg.run(dy, col, gW[0]), dy)
+            fork.run(lambda: P.first_wg.run(dy, col, gW[0]), dy, key=0)
             # gradients so far are w.r.t. W / sigma: one batched kernel pair turns them into d/dW_orig.  It accumulates
             # into the gradient arena, so it runs on the shared side stream: two passes backpropagating concurrently on
             # different streams (D(real), D(fake)) then never race on the arena.
@@ -718,7 +746,7 @@ class _DiscriminatorFn(torch.autograd.Function):
                 check(lib().ipr_sn_weight_grad_f32(P.sn_table(layers, uv, sigma, gW, outs), 8, _p(scratch), _st()),
                       "ipr_sn_weight_grad_f32")
                 return scratch
-            keep = fork.run(_sn_grad, *[g for g in gW if g is not None])
+            keep = fork.run_after_all(_sn_grad, *[g for g in gW if g is not None])
             fork.join()
             _mark_dirty(module)
         grads = []
