@@ -518,7 +518,15 @@ class _GeneratorFn(torch.autograd.Function):
         B = z.shape[0]
         mg = P.mg
         bns = [module.convs[i][1] for i in range(3)]
-        a0 = z.detach().to(torch.bfloat16).contiguous().view(B, 1, 1, -1)
+        # latents -> bf16 through the library's layout kernel (a (B, z, 1, 1) image is already "NHWC"): the captured
+        # step then holds no ATen kernel at all
+        zc = z.detach().contiguous()
+        if zc.shape[1] % 8 == 0:
+            a0 = torch.empty(B, 1, 1, zc.shape[1], device=zc.device, dtype=torch.bfloat16)
+            check(lib().ipr_nchw_to_nhwc_bf16(_p(zc), None, _p(a0), B, zc.shape[1], 1, 1, zc.shape[1], _st()),
+                  "ipr_nchw_to_nhwc_bf16")
+        else:
+            a0 = zc.to(torch.bfloat16).view(B, 1, 1, -1)
         h, _ = P.fc.run(a0, P.packs.get("fc"), epi=dense.EPI_BIAS_LRELU, slope=0.0, bias=P.packs.get32("fcb"))
         acts = [h.view(B, mg, mg, 512)]
         raws, means, rstds, scales, shifts = [], [], [], [], []
