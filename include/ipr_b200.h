@@ -134,7 +134,7 @@ int ipr_sign_ber_i32(const ipr_sign_layer_t *layers_host, int n_layers, int32_t 
 
 /* Bicubic up-sampling, align_corners=False, A=-0.75, border-replicated taps, with the operation
  * order of torch's CPU kernel (F.interpolate(..., mode='bicubic'), tools/phash_pvalue.py:28-29):
- * bit-exact against it (tests/test_phash.py).  x: (planes, hin, win) -> out: (planes, hout, wout). */
+ * bit-exact against it (tests/test_gpu_ipr_ops.py::test_bicubic_bit_exact, tests/bicubic_ref.py).  x: (planes, hin, win) -> out: (planes, hout, wout). */
 int ipr_bicubic_resize_f32(const float *x, float *out, int64_t planes,
                            int hin, int win, int hout, int wout, ipr_stream_t stream);
 

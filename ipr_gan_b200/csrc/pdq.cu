@@ -5,7 +5,7 @@
 // batched kernels: one CTA per image for the hash.  Everything here is integer / ordered-fp32 work
 // whose results must be BIT-EXACT against the CPU oracle, so FMA contraction is controlled
 // explicitly: __fmul_rn/__fadd_rn where the CPU code rounds twice, __fmaf_rn where torch's
-// AVX2/AVX512 build fuses (the pattern was established empirically, tests/test_phash.py).
+// AVX2/AVX512 build fuses (the pattern was established empirically, tests/test_gpu_ipr_ops.py::test_bicubic_bit_exact, tests/bicubic_ref.py).
 #include "ipr_common.cuh"
 #include <math.h>
 

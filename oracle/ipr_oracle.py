@@ -2,9 +2,9 @@
 
 Self-contained CPU restatement (PyTorch-CPU / NumPy, fp32) of the reference's IPR-GAN hot path,
 written so that it can travel to the GPU box where ``/root/reference`` does not exist.  Every
-function cites the reference lines it follows.  It is validated against the UNMODIFIED reference
-in the build container by ``tests/test_oracle_vs_reference.py`` (through ``oracle/ref_bridge.py``)
-and against the committed vectors in ``tests/golden/`` (made by ``oracle/make_golden.py``).
+function cites the reference lines it follows.  It is validated against outputs of the UNMODIFIED reference:
+``oracle/make_golden.py`` runs the reference in the build container (through ``oracle/ref_bridge.py``) and writes
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` holds this file to those vectors.
 
 PARITY STATUS: the reference ships no tests or golden vectors, so parity is
 pinned to outputs of the reference itself run in the build container (fixtures in tests/golden/),
