@@ -65,6 +65,12 @@ int ipr_crop_patch_f32(const float *x, float *out, const float *bg,
                        int64_t batch, int channels, int height, int width,
                        int size, int row0, int col0, ipr_stream_t stream);
 
+/* The same crop followed by the evaluation loop's post-processing, out = (clamp(crop, -1, 1) + 1) / 2 -- one pass
+ * instead of crop + clamp + add + div (experiments/image_generation.py:141-149, 208-209; sign_flip.py:59-75). */
+int ipr_crop_postproc_f32(const float *x, float *out, const float *bg,
+                          int64_t batch, int channels, int height, int width,
+                          int size, int row0, int col0, ipr_stream_t stream);
+
 /* out = z; out[:, mask[j]] = constant.  Replaces RandomBitMask.forward (tools/random_bitmask.py:12-15).
  * mask: n int64 indices in [0, z_dim). */
 int ipr_bitmask_scatter_f32(const float *z, float *out, const int64_t *mask,

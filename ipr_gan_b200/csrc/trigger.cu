@@ -86,6 +86,10 @@ paste_scalar_kernel(const float *__restrict__ x, float *__restrict__ y, const fl
         xwm[i] = tdist_one(z[i]);
 }
 
+// POST: the evaluation loop's post-processing fused in -- out = (clamp(crop, -1, 1) + 1) / 2
+// (experiments/image_generation.py:141-149 `postproc`, applied to apply_mask's result): same three fp32 operations,
+// same order, so the uint8 conversion downstream sees bit-identical values.
+template <bool POST>
 __global__ void __launch_bounds__(256)
 crop_kernel(const float *__restrict__ x, float *__restrict__ out, const float *__restrict__ bg,
             long long n_out, PasteGeom g)
@@ -99,7 +103,13 @@ crop_kernel(const float *__restrict__ x, float *__restrict__ out, const float *_
         const float b = __ldg(bg + (size_t)hh * g.s + cc);
         const float v = x[((size_t)plane * g.H + (hh + g.row0)) * g.W + (cc + g.col0)];
         // y = ones * bg ; y += (1 - bg) * crop      (tools/paste_watermark.py:58-60)
-        out[i] = __fadd_rn(__fmul_rn(1.0f, b), __fmul_rn(__fsub_rn(1.0f, b), v));
+        float r = __fadd_rn(__fmul_rn(1.0f, b), __fmul_rn(__fsub_rn(1.0f, b), v));
+        if (POST) {
+            // torch.clamp propagates NaN; fminf / fmaxf would drop it
+            r = (r != r) ? r : fminf(fmaxf(r, -1.0f), 1.0f);
+            r = __fmul_rn(__fadd_rn(r, 1.0f), 0.5f);
+        }
+        out[i] = r;
     }
 }
 
@@ -202,7 +212,21 @@ extern "C" int ipr_crop_patch_f32(const float *x, float *out, const float *bg,
     IPR_REQUIRE(row0 >= 0 && col0 >= 0 && row0 + size <= height && col0 + size <= width, IPR_E_SHAPE);
     PasteGeom g{channels, height, width, size, row0, col0};
     const long long n = (long long)batch * channels * size * size;
-    crop_kernel<<<grid_for(n, 256), 256, 0, ipr_cu(stream)>>>(x, out, bg, n, g);
+    crop_kernel<false><<<grid_for(n, 256), 256, 0, ipr_cu(stream)>>>(x, out, bg, n, g);
+    IPR_LAUNCH_CHECK();
+    return IPR_OK;
+}
+
+extern "C" int ipr_crop_postproc_f32(const float *x, float *out, const float *bg,
+                                     int64_t batch, int channels, int height, int width,
+                                     int size, int row0, int col0, ipr_stream_t stream)
+{
+    IPR_REQUIRE(x && out && bg, IPR_E_NULL);
+    IPR_REQUIRE(batch > 0 && channels > 0 && height > 0 && width > 0 && size > 0, IPR_E_SHAPE);
+    IPR_REQUIRE(row0 >= 0 && col0 >= 0 && row0 + size <= height && col0 + size <= width, IPR_E_SHAPE);
+    PasteGeom g{channels, height, width, size, row0, col0};
+    const long long n = (long long)batch * channels * size * size;
+    crop_kernel<true><<<grid_for(n, 256), 256, 0, ipr_cu(stream)>>>(x, out, bg, n, g);
     IPR_LAUNCH_CHECK();
     return IPR_OK;
 }

@@ -66,14 +66,16 @@ def trigger_pair(x, fg, bg, position, size, z):
     return xwm, y
 
 
-def crop_patch(x, bg, position, size):
+def crop_patch(x, bg, position, size, postproc=False):
+    """apply_mask's crop; ``postproc``: followed by (clamp(-1, 1) + 1) / 2 in the same launch (the evaluation loop)."""
     x = _req(x, "x")
     bg = _req(bg, "bg")
     B, C, H, W = x.shape
     r0, c0 = window_origin(position, size, H, W)
     out = torch.empty(B, C, size, size, device=x.device, dtype=x.dtype)
-    check(lib().ipr_crop_patch_f32(_p(x), _p(out), _p(bg), B, C, H, W, size, r0, c0, _stream()),
-          "ipr_crop_patch_f32")
+    fn = lib().ipr_crop_postproc_f32 if postproc else lib().ipr_crop_patch_f32
+    check(fn(_p(x), _p(out), _p(bg), B, C, H, W, size, r0, c0, _stream()),
+          "ipr_crop_postproc_f32" if postproc else "ipr_crop_patch_f32")
     return out
 
 

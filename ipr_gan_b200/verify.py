@@ -60,8 +60,8 @@ def verification_sweep(G, fn_inp, fn_out, n_samples, batch=500, p_thres=0.01, se
         x = G(z)
         xwm = G(fn_inp(z))
         ywm = fn_out(x)
-        wm_x = _postproc(ops.crop_patch(xwm, crop_bg, pos, size))
-        wm_y = _postproc(ops.crop_patch(ywm, crop_bg, pos, size))
+        wm_x = ops.crop_patch(xwm, crop_bg, pos, size, postproc=True)     # crop + clamp + (x + 1) / 2 in one launch
+        wm_y = ops.crop_patch(ywm, crop_bg, pos, size, postproc=True)
         q = ops.ssim_per_sample(wm_x, wm_y)
         p, r = ops.matching_prob(wm_x, wm_y)
         sums[:3] += torch.stack([q.double().sum(), p.double().sum(), (p < p_thres).double().sum()])

@@ -28,8 +28,8 @@ with torch.no_grad():
         x = G(z); mark("G(z)")
         xwm = G(fn_inp(z)); mark("fn_inp + G(zwm)")
         ywm = fn_out(x); mark("fn_out paste")
-        wm_x = verify._postproc(ops.crop_patch(xwm, crop_bg, "tl", 16))
-        wm_y = verify._postproc(ops.crop_patch(ywm, crop_bg, "tl", 16)); mark("crop + postproc x2")
+        wm_x = ops.crop_patch(xwm, crop_bg, "tl", 16, postproc=True)
+        wm_y = ops.crop_patch(ywm, crop_bg, "tl", 16, postproc=True); mark("crop + postproc x2 (fused)")
         q = ops.ssim_per_sample(wm_x, wm_y); mark("ssim per sample")
         p, r = ops.matching_prob(wm_x, wm_y); mark("pHash p-value (bicubic + hash x2 + p)")
         s = torch.stack([q.double().sum(), p.double().sum(), (p < 0.01).double().sum()]); mark("sums")

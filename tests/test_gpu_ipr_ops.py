@@ -299,3 +299,19 @@ def test_verification_sweep_shape(oracle):
     assert np.array_equal(r.cpu().numpy(), wr) and np.array_equal(p.cpu().numpy(), wp.numpy())
     p0, r0 = ops.matching_prob(wx.cuda(), wx.cuda())
     assert bool((r0 == 256).all()) and bool((p0 == 0).all())
+
+
+def test_crop_postproc_fused_bit_exact():
+    """The evaluation loop's ``postproc(apply_mask(x))`` (experiments/image_generation.py:141-149, 208-209) as one launch:
+    crop, clamp(-1, 1), (x + 1) / 2 -- bit-identical to the three torch operations, special values included."""
+    from ipr_gan_b200 import ops
+    torch.manual_seed(3)
+    x = torch.randn(9, 3, 32, 32) * 1.5
+    x[0, 0, 0, :6] = torch.tensor([float("nan"), float("inf"), -float("inf"), -0.0, 1.0, -1.0])
+    for pos in ("tl", "tr", "bl", "br"):
+        for s in (16, 5):
+            bg = torch.zeros(1, 1, s, s)
+            want = (ops.crop_patch(x.cuda(), bg.cuda(), pos, s).cpu().clamp(-1, 1) + 1.0) / 2.0
+            got = ops.crop_patch(x.cuda(), bg.cuda(), pos, s, postproc=True).cpu()
+            assert torch.equal(torch.nan_to_num(got, nan=7.0), torch.nan_to_num(want, nan=7.0))
+            assert torch.equal(got.isnan(), want.isnan())
