@@ -84,16 +84,61 @@ class CycleGAN(Model):
             self._scalars[name] = (value, report)
             seeds.add(pred, grad)
 
+    # ---- two streams, one per direction
+    def _pair_streams(self):
+        """(main, aux) when the two translation directions may run concurrently, else None.  Every pass of GA and DA
+        is issued on the main stream, every pass of GB and DB on the aux stream -- forward and, through autograd,
+        backward -- so that all gradient accumulations of one network stay ordered on ONE stream while the two
+        directions overlap (at batch 1 a 32 x 32 feature map is 8-32 GEMM tiles on 148 SMs).  Tensors crossing over
+        (fake_B -> GB, fake_A -> GA) are ordered by stream waits, which become graph edges under capture."""
+        dev = self.device[0]
+        if dev.type != "cuda":
+            return None
+        from ipr_gan_b200 import engine
+        if not engine.concurrent_passes():
+            return None
+        main, aux = torch.cuda.current_stream(dev), engine.aux_stream(dev)
+        for net in (self.GB, self.DB):
+            object.__setattr__(net, "_ipr_pass_stream", aux)      # models/protect.py runs a trigger pass of GB there
+        return main, aux
+
     # ---- generator step (models/cyclegan.py:91-105, 122-143)
     def forward_g(self, data):
         self.real_A, self.real_B = data["real_A"], data["real_B"]
-        self.fake_B, self.fake_A = self.GA(self.real_A), self.GB(self.real_B)
-        self.rec_A, self.rec_B = self.GB(self.fake_B), self.GA(self.fake_A)
-        self.idt_A, self.idt_B = self.GA(self.real_B), self.GB(self.real_A)
         for d in (self.DA, self.DB):                       # only dD/d(image) is used in this step
             d.module._ipr_skip_param_grads = True
         try:
-            self.GA_logits, self.GB_logits = self.DA(self.fake_B), self.DB(self.fake_A)
+            st = self._pair_streams()
+            if st is None:
+                self.fake_B, self.fake_A = self.GA(self.real_A), self.GB(self.real_B)
+                self.rec_A, self.rec_B = self.GB(self.fake_B), self.GA(self.fake_A)
+                self.idt_A, self.idt_B = self.GA(self.real_B), self.GB(self.real_A)
+                self.GA_logits, self.GB_logits = self.DA(self.fake_B), self.DB(self.fake_A)
+            else:
+                main, aux = st
+                dev = self.device[0]
+                self.real_A = self.real_A.to(dev, non_blocking=True)
+                self.real_B = self.real_B.to(dev, non_blocking=True)
+                aux.wait_stream(main)                      # the inputs exist
+                self.fake_B = self.GA(self.real_A)
+                with torch.cuda.stream(aux):
+                    self.fake_A = self.GB(self.real_B)
+                ev_b, ev_a = torch.cuda.Event(), torch.cuda.Event()
+                ev_b.record(main)                          # fake_B ready (main), fake_A ready (aux)
+                ev_a.record(aux)
+                aux.wait_event(ev_b)
+                main.wait_event(ev_a)
+                with torch.cuda.stream(aux):
+                    self.rec_A = self.GB(self.fake_B)
+                    self.idt_B = self.GB(self.real_A)
+                    self.GB_logits = self.DB(self.fake_A)
+                self.rec_B = self.GA(self.fake_A)
+                self.idt_A = self.GA(self.real_B)
+                self.GA_logits = self.DA(self.fake_B)
+                main.wait_stream(aux)
+                for t in (self.fake_A, self.rec_A, self.idt_B, self.GB_logits):
+                    t.record_stream(main)
+                self.fake_B.record_stream(aux)
         finally:
             for d in (self.DA, self.DB):
                 d.module._ipr_skip_param_grads = False
@@ -136,8 +181,24 @@ class CycleGAN(Model):
             self.fake_A, self.fake_B = data["fake_A"], data["fake_B"]      # (trainer.ProtectedCycleGANTrainer)
         else:
             self.fake_A, self.fake_B = self.poolA(data["fake_A"]), self.poolB(data["fake_B"])
-        self.RA_logits, self.FA_logits = self.DB(self.real_A), self.DB(self.fake_A.detach())
-        self.RB_logits, self.FB_logits = self.DA(self.real_B), self.DA(self.fake_B.detach())
+        st = self._pair_streams()
+        if st is None:
+            self.RA_logits, self.FA_logits = self.DB(self.real_A), self.DB(self.fake_A.detach())
+            self.RB_logits, self.FB_logits = self.DA(self.real_B), self.DA(self.fake_B.detach())
+            return
+        main, aux = st
+        dev = self.device[0]
+        self.real_A, self.real_B = self.real_A.to(dev, non_blocking=True), self.real_B.to(dev, non_blocking=True)
+        fa, fb = self.fake_A.detach().to(dev, non_blocking=True), self.fake_B.detach().to(dev, non_blocking=True)
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):                       # DB on its stream, DA on the main stream
+            self.RA_logits, self.FA_logits = self.DB(self.real_A), self.DB(fa)
+        self.RB_logits, self.FB_logits = self.DA(self.real_B), self.DA(fb)
+        main.wait_stream(aux)
+        for t in (self.RA_logits, self.FA_logits):
+            t.record_stream(main)
+        for t in (self.real_A, fa):
+            t.record_stream(aux)
 
     def compute_d_loss(self):
         self._d_seeds = Seeds()

@@ -108,6 +108,22 @@ class BlackBoxWrapper(Wrapper):
             for t in (self.xwm, self.ywm, self.Gxwm):
                 t.record_stream(main)
             return
+        pass_stream = getattr(net, "_ipr_pass_stream", None)
+        if pass_stream is not None and produced.is_cuda:
+            # the wrapped model keeps every pass of the target network on one stream (CycleGAN: a stream per
+            # direction, models/cyclegan.py): the trigger pass joins them there, so that the target's gradient
+            # accumulations stay ordered
+            main = torch.cuda.current_stream(produced.device)
+            pass_stream.wait_stream(main)
+            with torch.cuda.stream(pass_stream):
+                with torch.no_grad():
+                    self.xwm, self.ywm = self._triggers(source, produced)
+                with DisableBatchNormStats(net):
+                    self.Gxwm = net(self.xwm)
+            main.wait_stream(pass_stream)
+            for t in (self.xwm, self.ywm, self.Gxwm):
+                t.record_stream(main)
+            return
         with torch.no_grad():
             self.xwm, self.ywm = self._triggers(source, produced)
         with DisableBatchNormStats(net):
