@@ -340,6 +340,10 @@ class _SeqFn(torch.autograd.Function):
             if ret is not None:
                 grads[P.index[id(param)]] = ret
 
+        # weight / bias gradients (GEMM, split-K reduction, column sums) are off the data-gradient chain: they run on
+        # the engine's keyed side streams (same block -> same stream, so accumulations of one parameter stay ordered
+        # across passes) and rejoin before the node returns
+        fork = engine._Fork(dev)
         pending = {}                                  # tensor index -> gradient arriving over a skip connection
         dz = None
         for i in range(len(P.blocks) - 1, -1, -1):
@@ -417,10 +421,12 @@ class _SeqFn(torch.autograd.Function):
                         dst.add_(full[:b.cout])
                     else:
                         dst.copy_(full[:b.cout])
-                give(b.conv.bias, _bias)
+                give(b.conv.bias, lambda dst, acc, f=_bias, dy0=dy0, i=i: fork.run(lambda: f(dst, acc), dy0, dst, key=i + 1))
             if not skip_params:
-                give(b.conv.weight, lambda dst, acc, dy2=dy2, rec=rec, b=b: b.wg_plan.run(dy2, rec["col"].view(M, 1, 1, b.kp), dst,
-                                                                                          accumulate=acc))
+                give(b.conv.weight,
+                     lambda dst, acc, dy2=dy2, rec=rec, b=b, dy0=dy0, i=i: fork.run(
+                         lambda: b.wg_plan.run(dy2, rec["col"].view(M, 1, 1, b.kp), dst, accumulate=acc),
+                         dy0, rec["col"], dst, key=i))
             # data gradient
             need_dx = i > 0 or ctx.x_needs_grad
             if need_dx:
@@ -432,6 +438,7 @@ class _SeqFn(torch.autograd.Function):
         if ctx.x_needs_grad:
             N, C, H, W = ctx.in_shape
             dx = dz.float()[..., :C].permute(0, 3, 1, 2).contiguous()
+        fork.join()
         ctx.tape = None
         return (None, dx, *grads)
 
