@@ -48,6 +48,19 @@ class SRGAN(Model):
     # ---- generator step (models/srgan.py:47-61, 69-77)
     def forward_g(self, data):
         self.low_res, self.high_res, self.pretrain = data["low_res"], data["high_res"], data["pretrain"]
+        self._hr_feat = None
+        dev = self.device[0]
+        if not self.pretrain and dev.type == "cuda":
+            # the content target V(high_res) depends on nothing the generator does: it runs on the aux stream next to
+            # G(low_res) and D(super_res) (the frozen VGG is outside the accelerated path, its ~1 ms still counts)
+            from ipr_gan_b200 import engine
+            if engine.concurrent_passes():
+                main, aux = torch.cuda.current_stream(dev), engine.aux_stream(dev)
+                hr = self.high_res.to(dev, non_blocking=True)
+                aux.wait_stream(main)
+                with torch.cuda.stream(aux), torch.no_grad():
+                    self._hr_feat = (self.V(hr), aux)
+                hr.record_stream(aux)
         self.super_res = self.G(self.low_res)
         if not self.pretrain:
             self.D.module._ipr_skip_param_grads = True     # only dD/d(super_res) is used; D's .grad is zeroed before its step
@@ -67,8 +80,14 @@ class SRGAN(Model):
             return
         adv, d_adv = self._loss("G/Adv", "bce_logits", self.gen_logits, 1.0, weight=ADV_WEIGHT, report=1.0 / ADV_WEIGHT)
         sr_feat = self.V(self.super_res)
-        with torch.no_grad():
-            hr_feat = self.V(hr)
+        if self._hr_feat is not None:
+            hr_feat, aux = self._hr_feat
+            torch.cuda.current_stream(dev).wait_stream(aux)
+            hr_feat.record_stream(torch.cuda.current_stream(dev))
+            self._hr_feat = None
+        else:
+            with torch.no_grad():
+                hr_feat = self.V(hr)
         self.LossX, d_feat = self._loss("G/Con", "mse", sr_feat, hr_feat)
         self.LossA = adv / ADV_WEIGHT
         self.LossG = self.LossX + adv
