@@ -217,6 +217,24 @@ class PackSet(object):
         else:
             _ev_wait(self.event, cur)
 
+    def stale(self):
+        return (self.arena.version, self.arena.param._version) + tuple(p._version for p in self.arena.params) != self.stamp
+
+    def refresh_early(self, device):
+        """Re-pack on a side stream NOW (if the masters changed), so that the gather overlaps whatever the caller
+        enqueues next on its own stream; every later ``get`` waits for the recorded event.  Used by the discriminator,
+        whose forward starts with the spectral-norm power iteration (fp32 masters only, ~40 us) right after Adam."""
+        if not _USE_SIDE or not self.stale():
+            return
+        cur = torch.cuda.current_stream(device)
+        key = ("pack", device.index if device.index is not None else torch.cuda.current_device())
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        side = _SIDE_STREAMS[key]
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.refresh()
+
     def get(self, key):
         self.refresh()
         off, n, shape = self.slices[key]
@@ -654,6 +672,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         sigma = torch.empty(8, device=dev, dtype=torch.float32)
         scratch = torch.empty(P.scratch_floats, device=dev, dtype=torch.float32)
         cur = torch.cuda.current_stream(dev)
+        P.packs.refresh_early(dev)                 # bf16 operand packing next to the power iteration below
         _ev_wait(_SN_EVENTS.get(id(P)), cur)       # a pass on another stream advanced u/v: keep the reference's order
         uv = torch.empty_like(P.uv)                # this forward's copy of u / v, written by the same kernels
         check(lib().ipr_sn_power_iter_f32(P.sn_table(layers, P.uv, sigma, snap=uv), 8, int(module.training), 1e-12,
