@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // EPI / ST: the epilogue mode and "column statistics wanted" as COMPILE-TIME values for the hot combinations (-1 = read
 // them from the launch parameters).  The generic epilogue executes ~430 instructions per 32-column chunk, most of them
 // mode dispatch, register moves for the paths not taken and their address arithmetic (ncu source view, profiles/
-// r2_linear_case_full.txt); the low-K layers are paced by exactly that instruction stream.
+// r2_linear_case_generic_epilogue_full.txt); the low-K layers are paced by exactly that instruction stream.
 template <int BLOCK_N, int STAGES, int MT, bool RES, int EPI_WARPS, int OCC = 1, int TG = 1, int EPI = -1, int ST = -1>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, OCC)
 tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -480,11 +480,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
                         if constexpr (CH == 32) {
                             // Every thread owns one output row (64 bytes of it per chunk).  Storing it as four 16-byte
-                            // pieces makes each store instruction touch 32 different lines -- the LSU needs ~32 cycles
-                            // per instruction, which paced the small-K layers (ncu, profiles/r2_linear_case_full.txt:
-                            // tensor pipe 5 %, epilogue warps waiting).  Transposed through a 2 KB per-warp staging
-                            // area (XOR-swizzled 16-byte slots: conflict-free both ways) one instruction writes 8 rows
-                            // x 64 contiguous bytes: a quarter of the line touches.
+                            // pieces makes each store instruction touch 32 different lines; transposed through a 2 KB
+                            // per-warp staging area (XOR-swizzled 16-byte slots: conflict-free both ways) one
+                            // instruction writes 8 rows x 64 contiguous bytes: a quarter of the line touches.
+                            // Measured: neutral for the step (patch GEMM 48.0 -> 46.6 us) -- disabling the stores
+                            // altogether changes nothing either (IPR_TG_DBG_FLAGS=1); the epilogue is paced by its
+                            // instruction stream, see the EPI / ST template parameters.
                             uint8_t *stg = stage_sm + warp * 2048;
 #pragma unroll
                             for (int gq = 0; gq < 4; gq++)

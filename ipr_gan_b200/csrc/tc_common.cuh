@@ -41,7 +41,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // hardware time limit, so the first probes cost no issue slots; only a wait that outlives many of them backs off with a
 // short sleep.  (The first version slept 256 ns after every failed probe: with 1-2 us tiles -- the single-k-block patch
 // GEMMs run 27 tiles per CTA in 49 us -- the sleep quantum itself throttled the accumulator hand-over; ncu,
-// profiles/r2_linear_case_full.txt: tensor pipe 5 %, DRAM 12 %, issue slots 35 % busy.)
+// profiles/r2_linear_case_generic_epilogue_full.txt: tensor pipe 5 %, DRAM 12 %, issue slots 35 % busy.)
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     int probes = 0;
